@@ -1,0 +1,176 @@
+/* qpcontrol_b200.h -- C ABI of libqpcontrol_b200.so
+ *
+ * Drop-in boundary for QPControl.jl's per-timestep control loop, batched over independent robot instances.
+ * The reference (tkoolen/QPControl.jl) is pure Julia and has no FFI of its own; the seam this library replaces is the
+ * controller functor `(controller)(tau, t, x)` (reference src/lowlevel/momentum.jl:41-81, src/highlevel/standing.jl:58-89)
+ * and everything it reaches: Parametron `solve!` (momentum.jl:58), the OSQP optimizer plugged in as type parameter `O`
+ * (momentum.jl:1,15-16,27) and the RigidBodyDynamics state queries of SURVEY.md 8(a) row a15.  The setup-time calls
+ * mirror the reference constructors one to one so a Julia shim (qpcontrol.jl_b200/julia/QPControlB200.jl) can `ccall`
+ * them from the same user-facing API.  Plain pointers and sizes only.
+ *
+ * Conventions: all reals are IEEE fp64; matrices are row-major; spatial vectors are (angular; linear)
+ * (reference src/tasks.jl:41-43, src/contacts.jl:84-88); bodies are indexed 0..nb-1 in topological order with -1 = world;
+ * a joint is identified with its successor body; floating joint q = (w,x,y,z,px,py,pz), v = (omega; v) in body frame.
+ * Every function returning int returns 0 on success and a negative error code otherwise; qpc_last_error() describes
+ * the last failure of the calling thread.  CUDA errors never cross the ABI as exceptions.
+ */
+#ifndef QPCONTROL_B200_H
+#define QPCONTROL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qpc_mechanism qpc_mechanism;   /* replaces RigidBodyDynamics.Mechanism (momentum.jl:15-17) */
+typedef struct qpc_controller qpc_controller; /* replaces MomentumBasedController{N,O,S} (momentum.jl:1-34) */
+
+/* joint types (RigidBodyDynamics: Revolute, Prismatic, QuaternionFloating, Fixed) */
+enum { QPC_REVOLUTE = 0, QPC_PRISMATIC = 1, QPC_QUAT_FLOATING = 2, QPC_FIXED = 3 };
+
+/* task kinds: the seven types of reference src/tasks.jl */
+enum {
+  QPC_TASK_SPATIAL = 0,        /* SpatialAccelerationTask   tasks.jl:3-44    */
+  QPC_TASK_ANGULAR = 1,        /* AngularAccelerationTask   tasks.jl:47-84   */
+  QPC_TASK_LINEAR = 2,         /* LinearAccelerationTask    tasks.jl:86-123  */
+  QPC_TASK_POINT = 3,          /* PointAccelerationTask     tasks.jl:125-171 */
+  QPC_TASK_JOINT = 4,          /* JointAccelerationTask     tasks.jl:173-189 */
+  QPC_TASK_MOMENTUM_RATE = 5,  /* MomentumRateTask          tasks.jl:192-236 */
+  QPC_TASK_LINEAR_MOMENTUM_RATE = 6 /* LinearMomentumRateTask tasks.jl:239-262 */
+};
+/* addtask! flavours (momentum.jl:99-117) */
+enum { QPC_MODE_HARD = 0, QPC_MODE_SCALAR_WEIGHT = 1, QPC_MODE_MATRIX_WEIGHT = 2 };
+
+/* per-instance solver status: OSQP's codes; checkstatus (momentum.jl:83-91) accepts SOLVED and SOLVED_INACCURATE */
+enum {
+  QPC_SOLVED = 1,
+  QPC_SOLVED_INACCURATE = 2,
+  QPC_PRIMAL_INFEASIBLE_INACCURATE = 3,
+  QPC_DUAL_INFEASIBLE_INACCURATE = 4,
+  QPC_MAX_ITER_REACHED = -2,
+  QPC_PRIMAL_INFEASIBLE = -3,
+  QPC_DUAL_INFEASIBLE = -4,
+  QPC_NON_FINITE = -8,
+  QPC_UNSOLVED = -10
+};
+
+/* error codes */
+enum { QPC_OK = 0, QPC_ERR_ARG = -1, QPC_ERR_CUDA = -2, QPC_ERR_STATE = -3, QPC_ERR_LIMIT = -4 };
+
+/* OSQPSettings.* attributes the reference sets (test/runtests.jl:35-43, notebooks/Standing controller.ipynb:66-71);
+ * defaults are OSQP 0.5.x's (qpc_default_settings). */
+typedef struct {
+  double rho, sigma, alpha;
+  double eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+  double adaptive_rho_tolerance;
+  int32_t max_iter, scaling, adaptive_rho, adaptive_rho_interval, check_termination;
+  int32_t reserved[3];
+} qpc_settings;
+
+/* solve_batch flags */
+enum {
+  QPC_HOST_PTRS = 0,   /* all batch pointers are host memory: the library stages through pinned buffers, copies H2D,
+                          runs, copies D2H and synchronises before returning */
+  QPC_DEVICE_PTRS = 1  /* all batch pointers are device memory on the controller's device: fully asynchronous on
+                          `stream` */
+};
+
+/* Inputs of one batched tick.  Replaces `x` of the functor (momentum.jl:41,57: x = [q; v]) plus the mutable per-tick
+ * fields the reference reads through Parameters: task `desired` (tasks.jl:40,82,121,165,186,232,260) and
+ * ContactPoint.weight / .maxnormalforce (contacts.jl:35-36,54-57,76). */
+typedef struct {
+  const double* q;          /* [B][nq] */
+  const double* v;          /* [B][nv] */
+  const double* desired;    /* [B][desired_stride] task desireds concatenated in addtask! order, or NULL = the
+                               values of qpc_set_task_desired; entries owned by the standing controller are ignored */
+  int64_t desired_stride;   /* >= ndes, or 0 to broadcast one row */
+  const double* contact_weight;         /* [B][contact_stride] or NULL = qpc_set_contact_params values */
+  const double* contact_maxnormalforce; /* [B][contact_stride] or NULL */
+  int64_t contact_stride;   /* >= ncontacts, or 0 to broadcast one row */
+} qpc_batch_in;
+
+/* Outputs of one batched tick: what the reference leaves in tau (momentum.jl:75-80), controller.result.vd (:62-64)
+ * and the per-point world-frame wrenches it sums into controller.contactwrenches (:65-72). Any pointer may be NULL. */
+typedef struct {
+  double* tau;       /* [B][nv]  floating-joint entries exactly 0 (momentum.jl:93-97) */
+  double* vdot;      /* [B][nv] */
+  double* wrench;    /* [B][ncontacts][6] world frame (angular; linear) */
+  int32_t* status;   /* [B] */
+  int32_t* iters;    /* [B] ADMM iterations */
+  double* residuals; /* [B][2] unscaled primal / dual residual (OSQP definition) of the QP the device solved */
+  int32_t* factorizations; /* [B] KKT factorisations = 1 + rho updates (OSQP info.rho_updates + 1) */
+} qpc_batch_out;
+
+int qpc_version(void);
+const char* qpc_last_error(void);
+int qpc_device_count(void);
+void qpc_default_settings(qpc_settings* s);
+
+/* ---- mechanism: RigidBodyDynamics.Mechanism as a flat tree --------------------------------------------------- */
+qpc_mechanism* qpc_mechanism_create(int32_t nb, const int32_t* parent, const int32_t* jtype,
+                                    const double* axis /*[nb][3]*/, const double* X_R /*[nb][9]*/,
+                                    const double* X_p /*[nb][3]*/, const double* mass /*[nb]*/,
+                                    const double* com /*[nb][3]*/, const double* inertia_origin /*[nb][9]*/,
+                                    const double gravity[3]);
+void qpc_mechanism_destroy(qpc_mechanism*);
+int qpc_mechanism_dims(const qpc_mechanism*, int32_t* nb, int32_t* nq, int32_t* nv);
+
+/* ---- controller setup: MomentumBasedController{N}(mechanism, optimizer; floatingjoint) (momentum.jl:15-33) ------- */
+qpc_controller* qpc_controller_create(qpc_mechanism*, int32_t N, int32_t floating_body /* -1 = fixed base */,
+                                      const qpc_settings*);
+void qpc_controller_destroy(qpc_controller*);
+/* addcontact!(controller, body, position, normal, mu) (momentum.jl:142-148, contacts.jl:38-69); returns index >= 0 */
+int qpc_add_contact(qpc_controller*, int32_t body, const double position[3], const double normal[3], double mu);
+/* contact.weight[] / contact.maxnormalforce[] defaults (contacts.jl:35-36; both start at 0 = disabled, :50) */
+int qpc_set_contact_params(qpc_controller*, int32_t contact, double weight, double maxnormalforce);
+/* addtask!(controller, task[, weight]) (momentum.jl:99-117); W is dim x dim for QPC_MODE_MATRIX_WEIGHT; index >= 0 */
+int qpc_add_task(qpc_controller*, int32_t kind, int32_t source_body, int32_t target_body, int32_t frame_body,
+                 const double point[3], int32_t joint, int32_t mode, double weight, const double* W);
+/* setdesired!(task, desired): default used when qpc_batch_in.desired is NULL */
+int qpc_set_task_desired(qpc_controller*, int32_t task, const double* desired);
+/* regularize!(controller, joint, weight) (momentum.jl:128-131) */
+int qpc_regularize(qpc_controller*, int32_t joint, double weight);
+/* StandingController's per-tick PD laws (standing.jl:58-85), evaluated on the device before the low-level tick */
+int qpc_standing_setup(qpc_controller*, int32_t linmom_task, int32_t pelvis_task, int32_t pelvis_body, int32_t njoints,
+                       const int32_t* joint_tasks, const int32_t* joints, const double* kp, const double* kd,
+                       const double* qref, double com_kp, double com_kd, double pelvis_kp, double pelvis_kd,
+                       const double comref[3]);
+int qpc_set_settings(qpc_controller*, const qpc_settings*);
+/* initialize! (momentum.jl:150-156): freezes the program, builds the device tables on `device` */
+int qpc_finalize(qpc_controller*, int32_t device);
+/* sizes: nq, nv, ndes, ncontacts, and the dims (n, m_general, n_box) of the condensed QP the device solves */
+int qpc_controller_dims(const qpc_controller*, int32_t* nq, int32_t* nv, int32_t* ndes, int32_t* ncontacts,
+                        int32_t* n, int32_t* mg, int32_t* nbox);
+
+/* ---- the control tick for B instances: (controller)(tau, t, x) (momentum.jl:41-81 / standing.jl:58-89) ------------ */
+int qpc_solve_batch(qpc_controller*, int64_t B, const qpc_batch_in*, const qpc_batch_out*, int32_t flags,
+                    void* stream /* cudaStream_t, QPC_DEVICE_PTRS only; NULL = default stream */);
+/* ensure workspaces for batches up to B exist (no allocation happens inside qpc_solve_batch afterwards) */
+int qpc_reserve(qpc_controller*, int64_t B);
+/* number of kernels launched by this controller so far */
+int64_t qpc_launch_count(const qpc_controller*);
+/* measurement hooks: when profiling is on, every tick records CUDA events around its three kernels on the launching
+ * stream; qpc_stage_times waits for the last tick and returns {assembly, ADMM, inverse dynamics} milliseconds */
+int qpc_set_profiling(qpc_controller*, int32_t on);
+int qpc_stage_times(qpc_controller*, double ms[3]);
+/* fp64 FMA throughput of the device in TFLOP/s (dependent-chain-free DFMA loop), the roofline denominator */
+int qpc_measure_fp64_peak(int32_t device, double* tflops);
+
+/* ---- stage-level entry points (parity tests; the tick above is their composition) -------------------------------- */
+/* kinematics + QP assembly only: writes the condensed QP of every instance (device or host pointers per flags):
+ * P [B][n*n], qv [B][n], G [B][mg*n], lg/ug [B][mg], lb/ub [B][nbox], desired_out [B][ndes] */
+int qpc_assemble_batch(qpc_controller*, int64_t B, const qpc_batch_in*, double* P, double* qv, double* G, double* lg,
+                       double* ug, double* lb, double* ub, double* desired_out, int32_t flags, void* stream);
+
+/* ---- raw batched dense QPs: min 1/2 x'Px + q'x  s.t. lg <= G x <= ug, lb <= x_tail <= ub
+ * where the box applies to the last nbox variables.  Pointers per flags. */
+int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t nbox, const double* P,
+                       const double* qv, const double* G, const double* lg, const double* ug, const double* lb,
+                       const double* ub, const qpc_settings*, double* x, double* y /*[B][mg+nbox]*/, int32_t* status,
+                       int32_t* iters, double* residuals, int32_t flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

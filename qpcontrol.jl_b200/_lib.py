@@ -1,0 +1,325 @@
+"""ctypes binding of libqpcontrol_b200.so (C ABI: include/qpcontrol_b200.h).
+
+There is no CPU fallback: `load()` raises if the shared library has not been built, and `DeviceController` raises if
+the CUDA runtime reports no device.  The same binding code can drive another library exporting the setup half of the
+ABI (the kernel-body emulation under tests/emu uses that, tests only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .controller import BatchResult
+from .program import OSQPSettings, Program
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libqpcontrol_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+HOST_PTRS, DEVICE_PTRS = 0, 1
+
+
+class qpc_settings(C.Structure):
+    _fields_ = [("rho", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double), ("eps_abs", C.c_double),
+                ("eps_rel", C.c_double), ("eps_prim_inf", C.c_double), ("eps_dual_inf", C.c_double),
+                ("adaptive_rho_tolerance", C.c_double), ("max_iter", C.c_int32), ("scaling", C.c_int32),
+                ("adaptive_rho", C.c_int32), ("adaptive_rho_interval", C.c_int32), ("check_termination", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
+
+    @staticmethod
+    def from_py(s: OSQPSettings) -> "qpc_settings":
+        out = qpc_settings()
+        for f in ("rho", "sigma", "alpha", "eps_abs", "eps_rel", "eps_prim_inf", "eps_dual_inf",
+                  "adaptive_rho_tolerance", "max_iter", "scaling", "adaptive_rho", "adaptive_rho_interval",
+                  "check_termination"):
+            setattr(out, f, getattr(s, f))
+        return out
+
+
+class qpc_batch_in(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("v", C.c_void_p), ("desired", C.c_void_p), ("desired_stride", C.c_int64),
+                ("contact_weight", C.c_void_p), ("contact_maxnormalforce", C.c_void_p), ("contact_stride", C.c_int64)]
+
+
+class qpc_batch_out(C.Structure):
+    _fields_ = [("tau", C.c_void_p), ("vdot", C.c_void_p), ("wrench", C.c_void_p), ("status", C.c_void_p),
+                ("iters", C.c_void_p), ("residuals", C.c_void_p), ("factorizations", C.c_void_p)]
+
+
+SETUP_SYMBOLS = ["qpc_version", "qpc_last_error", "qpc_device_count", "qpc_default_settings", "qpc_mechanism_create",
+                 "qpc_mechanism_destroy", "qpc_mechanism_dims", "qpc_controller_create", "qpc_controller_destroy",
+                 "qpc_add_contact", "qpc_set_contact_params", "qpc_add_task", "qpc_set_task_desired", "qpc_regularize",
+                 "qpc_standing_setup", "qpc_set_settings", "qpc_finalize", "qpc_controller_dims"]
+COMPUTE_SYMBOLS = ["qpc_solve_batch", "qpc_reserve", "qpc_launch_count", "qpc_assemble_batch", "qpc_solve_qp_batch",
+                   "qpc_set_profiling", "qpc_stage_times", "qpc_measure_fp64_peak"]
+
+_libs = {}
+
+
+def load(path: Optional[str] = None):
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; "
+                           f"g.build()' or make -C qpcontrol.jl_b200/csrc). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.qpc_last_error.restype = C.c_char_p
+    lib.qpc_mechanism_create.restype = C.c_void_p
+    lib.qpc_controller_create.restype = C.c_void_p
+    if hasattr(lib, "qpc_launch_count"):
+        lib.qpc_launch_count.restype = C.c_int64
+    _libs[path] = lib
+    return lib
+
+
+def _c(a, dtype=np.float64):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+def _p(a):
+    # data_as keeps a reference to the array alive for as long as the pointer object lives
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def check(lib, code: int, what: str):
+    if code < 0:
+        raise RuntimeError(f"{what} failed ({code}): {lib.qpc_last_error().decode()}")
+    return code
+
+
+class Handles:
+    """Mechanism + controller handles built from a recorded Program through the setup half of the C ABI."""
+
+    def __init__(self, lib, program: Program, device: int = 0):
+        self.lib = lib
+        self.program = program
+        m = program.mechanism
+        arrs = [_c(m.parent, np.int32), _c(m.jtype, np.int32), _c(m.axis), _c(m.X_R), _c(m.X_p), _c(m.mass),
+                _c(m.com), _c(m.inertia_origin()), _c(m.gravity)]
+        self.mech = C.c_void_p(lib.qpc_mechanism_create(C.c_int32(m.nb), *[_p(a) for a in arrs]))
+        if not self.mech:
+            raise RuntimeError("qpc_mechanism_create failed: " + lib.qpc_last_error().decode())
+        st = qpc_settings.from_py(program.settings)
+        self.ctrl = C.c_void_p(lib.qpc_controller_create(self.mech, C.c_int32(program.N),
+                                                         C.c_int32(program.floating_body), C.byref(st)))
+        if not self.ctrl:
+            raise RuntimeError("qpc_controller_create failed: " + lib.qpc_last_error().decode())
+        for kind, idx in program.events:
+            if kind == "contact":
+                c = program.contacts[idx]
+                got = check(lib, lib.qpc_add_contact(self.ctrl, C.c_int32(c.body), _p(_c(c.position)),
+                                                     _p(_c(c.normal)), C.c_double(c.mu)), "qpc_add_contact")
+                assert got == idx
+            else:
+                e = program.tasks[idx]
+                t = e.task
+                got = check(lib, lib.qpc_add_task(self.ctrl, C.c_int32(t.kind), C.c_int32(t.source),
+                                                  C.c_int32(t.target), C.c_int32(t.frame), _p(_c(np.array(t.point))),
+                                                  C.c_int32(t.joint), C.c_int32(e.mode), C.c_double(e.weight),
+                                                  _p(_c(e.W))), "qpc_add_task")
+                assert got == idx
+        for j in range(m.nb):
+            r = m.velocity_range(j)
+            if len(r) and program.reg[r[0]] != 0.0:
+                check(lib, lib.qpc_regularize(self.ctrl, C.c_int32(j), C.c_double(float(program.reg[r[0]]))),
+                      "qpc_regularize")
+        s = program.standing
+        if s is not None:
+            check(lib, lib.qpc_standing_setup(
+                self.ctrl, C.c_int32(s.linmom_task), C.c_int32(s.pelvis_task), C.c_int32(s.pelvis_body),
+                C.c_int32(len(s.joints)), _p(_c(s.joint_tasks, np.int32)), _p(_c(s.joints, np.int32)),
+                _p(_c(s.joint_kp)), _p(_c(s.joint_kd)), _p(_c(s.joint_ref)), C.c_double(s.com_kp),
+                C.c_double(s.com_kd), C.c_double(s.pelvis_kp), C.c_double(s.pelvis_kd), _p(_c(s.comref))),
+                "qpc_standing_setup")
+        check(lib, lib.qpc_finalize(self.ctrl, C.c_int32(device)), "qpc_finalize")
+        self.sync_defaults()
+        dims = [C.c_int32() for _ in range(7)]
+        check(lib, lib.qpc_controller_dims(self.ctrl, *[C.byref(d) for d in dims]), "qpc_controller_dims")
+        self.nq, self.nv, self.ndes, self.ncontacts, self.n, self.mg, self.nbox = [d.value for d in dims]
+
+    def sync_defaults(self):
+        """Push the current `setdesired!` values and ContactPoint.weight / .maxnormalforce (mutable between ticks in
+        the reference) and the solver settings."""
+        lib, pr = self.lib, self.program
+        for i, c in enumerate(pr.contacts):
+            check(lib, lib.qpc_set_contact_params(self.ctrl, C.c_int32(i), C.c_double(c.weight),
+                                                  C.c_double(c.maxnormalforce)), "qpc_set_contact_params")
+        for i, e in enumerate(pr.tasks):
+            check(lib, lib.qpc_set_task_desired(self.ctrl, C.c_int32(i), _p(_c(e.task.desired))),
+                  "qpc_set_task_desired")
+        st = qpc_settings.from_py(pr.settings)
+        check(lib, lib.qpc_set_settings(self.ctrl, C.byref(st)), "qpc_set_settings")
+
+    def close(self):
+        if getattr(self, "ctrl", None):
+            self.lib.qpc_controller_destroy(self.ctrl)
+            self.ctrl = None
+        if getattr(self, "mech", None):
+            self.lib.qpc_mechanism_destroy(self.mech)
+            self.mech = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- argument marshalling shared by every compute entry point ----------------------------------------------
+    def batch_in(self, q, v, desired, cw, cm, ptr=lambda a: a.ctypes.data, keep=None):
+        """Builds a qpc_batch_in from arrays (numpy for host pointers; `ptr` extracts the address)."""
+        bi = qpc_batch_in()
+        bi.q, bi.v = ptr(q), ptr(v)
+        bi.desired = None if desired is None else ptr(desired)
+        bi.desired_stride = 0 if desired is None or desired.ndim == 1 else desired.shape[1]
+        if (cw is None) != (cm is None):
+            raise ValueError("give both contact_weight and contact_maxnormalforce or neither")
+        bi.contact_weight = None if cw is None else ptr(cw)
+        bi.contact_maxnormalforce = None if cm is None else ptr(cm)
+        bi.contact_stride = 0 if cw is None or cw.ndim == 1 else cw.shape[1]
+        return bi
+
+
+def _prep_host_inputs(h: Handles, q, v, desired, cw, cm):
+    q, v = np.atleast_2d(_c(q)), np.atleast_2d(_c(v))
+    B = q.shape[0]
+    if q.shape != (B, h.nq) or v.shape != (B, h.nv):
+        raise ValueError(f"q must be [B,{h.nq}] and v [B,{h.nv}]")
+    desired = _c(desired)
+    if desired is not None and desired.shape[-1] != h.ndes:
+        raise ValueError(f"desired must have {h.ndes} columns")
+    cw, cm = _c(cw), _c(cm)
+    if cw is not None and cm is None:
+        cm = np.array([c.maxnormalforce for c in h.program.contacts])
+    if cm is not None and cw is None:
+        cw = np.array([c.weight for c in h.program.contacts])
+    if cw is not None and cw.ndim != cm.ndim:
+        if cw.ndim == 1:
+            cw = np.ascontiguousarray(np.broadcast_to(cw, cm.shape))
+        else:
+            cm = np.ascontiguousarray(np.broadcast_to(cm, cw.shape))
+    return q, v, desired, cw, cm, B
+
+
+def _alloc_out(h: Handles, B):
+    return BatchResult(tau=np.zeros((B, h.nv)), vdot=np.zeros((B, h.nv)), wrenches=np.zeros((B, h.ncontacts, 6)),
+                       status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32), residuals=np.zeros((B, 2)))
+
+
+def _batch_out(res: BatchResult, ptr=lambda a: a.ctypes.data):
+    bo = qpc_batch_out()
+    bo.tau, bo.vdot, bo.wrench = ptr(res.tau), ptr(res.vdot), ptr(res.wrenches)
+    bo.status, bo.iters, bo.residuals = ptr(res.status), ptr(res.iters), ptr(res.residuals)
+    return bo
+
+
+class DeviceController:
+    """The CUDA controller behind `MomentumBasedController.finalize()`."""
+
+    def __init__(self, program: Program, device: int = 0):
+        self.lib = load()
+        ndev = self.lib.qpc_device_count()
+        if ndev <= 0:
+            raise RuntimeError("no CUDA device visible: the qpcontrol_b200 hot path has no CPU fallback")
+        self.h = Handles(self.lib, program, device)
+        self.program = program
+        self.device = device
+
+    @property
+    def dims(self):
+        return dict(nq=self.h.nq, nv=self.h.nv, ndes=self.h.ndes, ncontacts=self.h.ncontacts, n=self.h.n,
+                    mg=self.h.mg, nbox=self.h.nbox)
+
+    def reserve(self, B: int):
+        check(self.lib, self.lib.qpc_reserve(self.h.ctrl, C.c_int64(B)), "qpc_reserve")
+
+    def launch_count(self) -> int:
+        return int(self.lib.qpc_launch_count(self.h.ctrl))
+
+    def set_profiling(self, on: bool):
+        check(self.lib, self.lib.qpc_set_profiling(self.h.ctrl, C.c_int32(int(on))), "qpc_set_profiling")
+
+    def stage_times(self):
+        """{assembly, ADMM, inverse dynamics} milliseconds of the last tick (CUDA events on the launching stream)."""
+        ms = (C.c_double * 3)()
+        check(self.lib, self.lib.qpc_stage_times(self.h.ctrl, ms), "qpc_stage_times")
+        return [ms[0], ms[1], ms[2]]
+
+    def solve_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None) -> BatchResult:
+        """Host numpy buffers in, host numpy buffers out (H2D + kernels + D2H inside the call)."""
+        h = self.h
+        h.sync_defaults()
+        q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
+        res = _alloc_out(h, B)
+        bi, bo = h.batch_in(q, v, desired, cw, cm), _batch_out(res)
+        check(self.lib, self.lib.qpc_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo), C.c_int32(HOST_PTRS),
+                                                 None), "qpc_solve_batch")
+        return res
+
+    def solve_device(self, B: int, q, v, out: dict, desired=None, contact_weight=None, contact_maxnormalforce=None,
+                     stream: int = 0):
+        """Device pointers in/out (torch CUDA tensors or anything with `.data_ptr()`), asynchronous on `stream`
+        (a raw cudaStream_t value).  `out` maps tau / vdot / wrench / status / iters / residuals to tensors."""
+        h = self.h
+        ptr = lambda t: t.data_ptr()  # noqa: E731
+        bi = qpc_batch_in()
+        bi.q, bi.v = ptr(q), ptr(v)
+        bi.desired = None if desired is None else ptr(desired)
+        bi.desired_stride = 0 if desired is None or desired.dim() == 1 else desired.shape[1]
+        bi.contact_weight = None if contact_weight is None else ptr(contact_weight)
+        bi.contact_maxnormalforce = None if contact_maxnormalforce is None else ptr(contact_maxnormalforce)
+        bi.contact_stride = 0 if contact_weight is None or contact_weight.dim() == 1 else contact_weight.shape[1]
+        bo = qpc_batch_out()
+        for name in ("tau", "vdot", "wrench", "status", "iters", "residuals", "factorizations"):
+            t = out.get(name)
+            setattr(bo, name, None if t is None else ptr(t))
+        check(self.lib, self.lib.qpc_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo),
+                                                 C.c_int32(DEVICE_PTRS), C.c_void_p(stream)), "qpc_solve_batch")
+
+    def assemble_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None):
+        """Stage-level entry point: the condensed QP of every instance."""
+        h = self.h
+        h.sync_defaults()
+        q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
+        out = dict(P=np.zeros((B, h.n, h.n)), q=np.zeros((B, h.n)), G=np.zeros((B, h.mg, h.n)),
+                   lg=np.zeros((B, h.mg)), ug=np.zeros((B, h.mg)), lb=np.zeros((B, h.nbox)), ub=np.zeros((B, h.nbox)),
+                   desired=np.zeros((B, h.ndes)))
+        bi = h.batch_in(q, v, desired, cw, cm)
+        check(self.lib, self.lib.qpc_assemble_batch(h.ctrl, C.c_int64(B), C.byref(bi), _p(out["P"]), _p(out["q"]),
+                                                    _p(out["G"]), _p(out["lg"]), _p(out["ug"]), _p(out["lb"]),
+                                                    _p(out["ub"]), _p(out["desired"]), C.c_int32(HOST_PTRS), None),
+              "qpc_assemble_batch")
+        return out
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    lib = load()
+    tf = C.c_double()
+    check(lib, lib.qpc_measure_fp64_peak(C.c_int32(device), C.byref(tf)), "qpc_measure_fp64_peak")
+    return tf.value
+
+
+def solve_qp_batch_host(P, qv, G, lg, ug, lb=None, ub=None, settings: Optional[OSQPSettings] = None, device: int = 0):
+    """Raw batched dense QPs through qpc_solve_qp_batch with host buffers."""
+    lib = load()
+    if lib.qpc_device_count() <= 0:
+        raise RuntimeError("no CUDA device visible: the qpcontrol_b200 hot path has no CPU fallback")
+    P, qv, G, lg, ug = (_c(a) for a in (P, qv, G, lg, ug))
+    B, n = qv.shape
+    mg = lg.shape[1]
+    nbox = 0 if lb is None else lb.shape[1]
+    lb = _c(lb) if nbox else np.zeros((B, 0))
+    ub = _c(ub) if nbox else np.zeros((B, 0))
+    st = qpc_settings.from_py(settings or OSQPSettings())
+    out = dict(x=np.zeros((B, n)), y=np.zeros((B, mg + nbox)), status=np.zeros(B, np.int32),
+               iters=np.zeros(B, np.int32), res=np.zeros((B, 2)))
+    check(lib, lib.qpc_solve_qp_batch(C.c_int32(device), C.c_int64(B), C.c_int32(n), C.c_int32(mg), C.c_int32(nbox),
+                                      _p(P), _p(qv), _p(G), _p(lg), _p(ug), _p(lb), _p(ub), C.byref(st), _p(out["x"]),
+                                      _p(out["y"]), _p(out["status"]), _p(out["iters"]), _p(out["res"]),
+                                      C.c_int32(HOST_PTRS), None), "qpc_solve_qp_batch")
+    return out

@@ -1,0 +1,570 @@
+// api.cu -- CUDA backend of the C ABI (include/qpcontrol_b200.h): kernels, workspaces, launches.
+// Built for sm_100a only:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ...   (see Makefile)
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <mutex>
+#include <vector>
+
+struct DeviceBuffers {
+  // QP workspace (both pointer modes)
+  double *P = nullptr, *qv = nullptr, *G = nullptr, *lg = nullptr, *ug = nullptr, *lb = nullptr, *ub = nullptr;
+  double *des = nullptr, *x = nullptr, *y = nullptr;
+  // staging for QPC_HOST_PTRS
+  double *q = nullptr, *v = nullptr, *desired = nullptr, *cw = nullptr, *cm = nullptr;
+  double *tau = nullptr, *vdot = nullptr, *wrench = nullptr, *res = nullptr;
+  int *status = nullptr, *iters = nullptr;
+  long long capB = 0, cap_desired = 0, cap_contact = 0;
+};
+struct Backend {
+  bool dirty = false;
+  int device = 0;
+  void* d_prog = nullptr;
+  cudaStream_t stream = nullptr;
+  DeviceBuffers buf;
+  std::atomic<long long> launches{0};
+  std::mutex mu;
+  bool profiling = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int* d_nfac = nullptr;  // [capB] factorisations per instance
+};
+
+#include "admm.cuh"
+#include "kin.cuh"
+#include "setup_api.h"
+
+using namespace qpc;
+
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return qpc_fail(QPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));               \
+  } while (0)
+
+// ---- kernels: one robot instance / one QP per CTA ----------------------------------------------------------------------
+constexpr int ASM_THREADS = 64;
+constexpr int ADMM_THREADS = 128;
+constexpr int ID_THREADS = 64;
+
+__global__ void __launch_bounds__(ASM_THREADS)
+qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb, long long B) {
+  extern __shared__ double smem[];
+  for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    KinSmem s = kin_layout(smem, pg->nb, pg->nq, pg->nv, pg->ndes, pg->ncontacts, pg->N);
+    kin_load(pg, io, inst, s);
+    kin_forward(pg, s);
+    kin_composite(pg, s);
+    kin_standing(pg, s);
+    kin_contacts(pg, s);
+    const int n = pg->n, mg = pg->mg, nbx = pg->nbx;
+    kin_assemble(pg, s, qb.P + inst * n * n, qb.qv + inst * n, qb.G + inst * mg * n, qb.lg + inst * mg,
+                 qb.ug + inst * mg, qb.lb + inst * nbx, qb.ub + inst * nbx);
+    for (int i = threadIdx.x; i < pg->ndes; i += blockDim.x) qb.des[inst * pg->ndes + i] = s.des[i];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(ADMM_THREADS)
+qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B) {
+  extern __shared__ double smem[];
+  for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    AdmmProblem pb;
+    pb.P = qb.P + inst * n * n;
+    pb.qv = qb.qv + inst * n;
+    pb.G = qb.G + inst * mg * n;
+    pb.lg = qb.lg + inst * mg;
+    pb.ug = qb.ug + inst * mg;
+    pb.lb = qb.lb + inst * nbx;
+    pb.ub = qb.ub + inst * nbx;
+    pb.x = qb.x + inst * n;
+    pb.y = qb.y ? qb.y + inst * (mg + nbx) : nullptr;
+    pb.status = qb.status + inst;
+    pb.iters = qb.iters ? qb.iters + inst : nullptr;
+    pb.res = qb.res ? qb.res + 2 * inst : nullptr;
+    pb.nfac = qb.nfac ? qb.nfac + inst : nullptr;
+    admm_solve(st, pb, n, mg, nbx, smem);
+  }
+}
+
+// status for programs whose QP has no free variable (everything fixed by hard joint tasks)
+__global__ void qpc_trivial_status_kernel(int* status, int* iters, double* res, long long B) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < B) {
+    status[i] = 1;
+    if (iters) iters[i] = 0;
+    if (res) res[2 * i] = res[2 * i + 1] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(ID_THREADS)
+qpc_inverse_dynamics_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb, double* tau, double* vdot,
+                            double* wrench, long long B) {
+  extern __shared__ double smem[];
+  for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    KinSmem s = kin_layout(smem, pg->nb, pg->nq, pg->nv, pg->ndes, pg->ncontacts, pg->N);
+    kin_load(pg, io, inst, s);
+    for (int i = threadIdx.x; i < pg->ndes; i += blockDim.x) s.des[i] = qb.des[inst * pg->ndes + i];
+    __syncthreads();
+    kin_forward(pg, s);
+    kin_contacts(pg, s);
+    double* tdst = tau ? tau + inst * pg->nv : s.q;  // tau is always computed; discard into dead scratch if unwanted
+    kin_inverse_dynamics(pg, s, qb.x + inst * pg->n, vdot ? vdot + inst * pg->nv : nullptr,
+                         wrench ? wrench + inst * pg->ncontacts * 6 : nullptr, tdst);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+template <class T>
+static cudaError_t grow(T*& p, long long count) {
+  if (p) cudaFree(p);
+  p = nullptr;
+  return cudaMalloc((void**)&p, sizeof(T) * (size_t)(count > 0 ? count : 1));
+}
+
+static int ensure_capacity(qpc_controller* c, long long B, long long dstride, long long cstride) {
+  DeviceBuffers& b = c->be.buf;
+  const DevProgram& p = c->prog;
+  if (B > b.capB) {
+    const long long n = p.n, mg = p.mg, nbx = p.nbx;
+    CUDA_TRY(grow(b.P, B * n * n));
+    CUDA_TRY(grow(b.qv, B * n));
+    CUDA_TRY(grow(b.G, B * mg * n));
+    CUDA_TRY(grow(b.lg, B * mg));
+    CUDA_TRY(grow(b.ug, B * mg));
+    CUDA_TRY(grow(b.lb, B * nbx));
+    CUDA_TRY(grow(b.ub, B * nbx));
+    CUDA_TRY(grow(b.des, B * p.ndes));
+    CUDA_TRY(grow(b.x, B * n));
+    CUDA_TRY(grow(b.y, B * (mg + nbx)));
+    CUDA_TRY(grow(b.q, B * p.nq));
+    CUDA_TRY(grow(b.v, B * p.nv));
+    CUDA_TRY(grow(b.tau, B * p.nv));
+    CUDA_TRY(grow(b.vdot, B * p.nv));
+    CUDA_TRY(grow(b.wrench, B * p.ncontacts * 6));
+    CUDA_TRY(grow(b.res, B * 2));
+    CUDA_TRY(grow(b.status, B));
+    CUDA_TRY(grow(b.iters, B));
+    CUDA_TRY(grow(c->be.d_nfac, B));
+    b.capB = B;
+    b.cap_desired = 0;
+    b.cap_contact = 0;
+  }
+  if (B * dstride > b.cap_desired) {
+    CUDA_TRY(grow(b.desired, B * dstride));
+    b.cap_desired = B * dstride;
+  }
+  if (B * cstride > b.cap_contact) {
+    CUDA_TRY(grow(b.cw, B * cstride));
+    CUDA_TRY(grow(b.cm, B * cstride));
+    b.cap_contact = B * cstride;
+  }
+  return QPC_OK;
+}
+
+static int upload_program(qpc_controller* c) {
+  if (!c->be.d_prog) CUDA_TRY(cudaMalloc(&c->be.d_prog, sizeof(DevProgram)));
+  CUDA_TRY(cudaMemcpyAsync(c->be.d_prog, &c->prog, sizeof(DevProgram), cudaMemcpyHostToDevice, c->be.stream));
+  CUDA_TRY(cudaStreamSynchronize(c->be.stream));
+  c->be.dirty = false;
+  return QPC_OK;
+}
+
+static int configure_kernels(const DevProgram& p) {
+  const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
+  const int asmem = admm_smem_doubles(p.n, p.mg, p.nbx) * 8;
+  if (ksm > 227 * 1024 || asmem > 227 * 1024)
+    return qpc_fail(QPC_ERR_LIMIT, "problem does not fit the 227 KB shared memory of one CTA");
+  CUDA_TRY(cudaFuncSetAttribute(qpc_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
+  CUDA_TRY(cudaFuncSetAttribute(qpc_inverse_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
+  CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
+  return QPC_OK;
+}
+
+static QpBuffers qp_view(const DeviceBuffers& b) {
+  QpBuffers q;
+  q.P = b.P;
+  q.qv = b.qv;
+  q.G = b.G;
+  q.lg = b.lg;
+  q.ug = b.ug;
+  q.lb = b.lb;
+  q.ub = b.ub;
+  q.des = b.des;
+  q.x = b.x;
+  q.y = b.y;
+  q.status = b.status;
+  q.iters = b.iters;
+  q.res = b.res;
+  return q;
+}
+
+static int launch_grid(long long B) { return (int)(B < (1ll << 30) ? B : (1ll << 30)); }
+
+// the tick on device pointers; asynchronous on `stream`
+static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* tau, double* vdot, double* wrench,
+                    int* status, int* iters, double* res, int* nfac, cudaStream_t stream) {
+  const DevProgram& p = c->prog;
+  const DevProgram* dp = (const DevProgram*)c->be.d_prog;
+  QpBuffers qb = qp_view(c->be.buf);
+  if (status) qb.status = status;
+  if (iters) qb.iters = iters;
+  if (res) qb.res = res;
+  qb.nfac = nfac ? nfac : c->be.d_nfac;
+  const bool prof = c->be.profiling;
+  const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
+  const int asmem = admm_smem_doubles(p.n, p.mg, p.nbx) * 8;
+  const int grid = launch_grid(B);
+  if (prof) cudaEventRecord(c->be.ev[0], stream);
+  qpc_assemble_kernel<<<grid, ASM_THREADS, ksm, stream>>>(dp, io, qb, B);
+  if (prof) cudaEventRecord(c->be.ev[1], stream);
+  if (p.n > 0)
+    qpc_admm_kernel<<<grid, ADMM_THREADS, asmem, stream>>>(p.settings, qb, p.n, p.mg, p.nbx, B);
+  else
+    qpc_trivial_status_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(qb.status, qb.iters, qb.res, B);
+  if (prof) cudaEventRecord(c->be.ev[2], stream);
+  qpc_inverse_dynamics_kernel<<<grid, ID_THREADS, ksm, stream>>>(dp, io, qb, tau, vdot, wrench, B);
+  if (prof) cudaEventRecord(c->be.ev[3], stream);
+  c->be.launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return QPC_OK;
+}
+
+extern "C" {
+
+int qpc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int qpc_finalize(qpc_controller* c, int32_t device) {
+  if (!c) return qpc_fail(QPC_ERR_ARG, "null controller");
+  if (c->finalized) return QPC_OK;
+  std::string err = compile_program(c->hc, c->prog);
+  if (!err.empty()) return qpc_fail(QPC_ERR_LIMIT, err);
+  c->be.device = device;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->be.stream, cudaStreamNonBlocking));
+  int rc = configure_kernels(c->prog);
+  if (rc) return rc;
+  rc = upload_program(c);
+  if (rc) return rc;
+  c->finalized = true;
+  return QPC_OK;
+}
+
+void qpc_controller_destroy(qpc_controller* c) {
+  if (!c) return;
+  if (c->finalized) {
+    cudaSetDevice(c->be.device);
+    DeviceBuffers& b = c->be.buf;
+    void* ptrs[] = {b.P, b.qv, b.G, b.lg, b.ug, b.lb, b.ub, b.des, b.x, b.y, b.q, b.v, b.desired, b.cw,
+                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac};
+    for (int i = 0; i < 4; i++)
+      if (c->be.ev[i]) cudaEventDestroy(c->be.ev[i]);
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+    if (c->be.stream) cudaStreamDestroy(c->be.stream);
+  }
+  delete c;
+}
+
+int qpc_reserve(qpc_controller* c, int64_t B) {
+  if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
+  std::lock_guard<std::mutex> lock(c->be.mu);
+  CUDA_TRY(cudaSetDevice(c->be.device));
+  return ensure_capacity(c, B, c->prog.ndes, c->prog.ncontacts);
+}
+
+int64_t qpc_launch_count(const qpc_controller* c) { return c ? (int64_t)c->be.launches.load() : 0; }
+
+int qpc_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const qpc_batch_out* out, int32_t flags,
+                    void* stream_) {
+  if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
+  if (!in || !out || !in->q || !in->v || B < 0) return qpc_fail(QPC_ERR_ARG, "qpc_solve_batch: bad arguments");
+  if (B == 0) return QPC_OK;
+  const DevProgram& p = c->prog;
+  if (in->desired && in->desired_stride != 0 && in->desired_stride < p.ndes)
+    return qpc_fail(QPC_ERR_ARG, "desired_stride smaller than the number of desired values");
+  if ((in->contact_weight == nullptr) != (in->contact_maxnormalforce == nullptr))
+    return qpc_fail(QPC_ERR_ARG, "contact_weight and contact_maxnormalforce must be given together");
+  if (in->contact_weight && in->contact_stride != 0 && in->contact_stride < p.ncontacts)
+    return qpc_fail(QPC_ERR_ARG, "contact_stride smaller than the number of contacts");
+  std::lock_guard<std::mutex> lock(c->be.mu);
+  CUDA_TRY(cudaSetDevice(c->be.device));
+  if (c->be.dirty) {
+    int rc = upload_program(c);
+    if (rc) return rc;
+  }
+  const long long dstride = in->desired ? in->desired_stride : 0, cstride = in->contact_weight ? in->contact_stride : 0;
+  const long long drows = dstride ? B : 1, crows = cstride ? B : 1;
+  int rc = ensure_capacity(c, B, in->desired ? (dstride ? dstride : p.ndes) : 0,
+                           in->contact_weight ? (cstride ? cstride : p.ncontacts) : 0);
+  if (rc) return rc;
+  DeviceBuffers& b = c->be.buf;
+  BatchIO io;
+  io.desired_stride = dstride;
+  io.contact_stride = cstride;
+  if (flags == QPC_DEVICE_PTRS) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    io.q = in->q;
+    io.v = in->v;
+    io.desired = in->desired;
+    io.cweight = in->contact_weight;
+    io.cmaxnf = in->contact_maxnormalforce;
+    return run_tick(c, B, io, out->tau, out->vdot, out->wrench, out->status, out->iters, out->residuals,
+                    out->factorizations, stream);
+  }
+  cudaStream_t s = c->be.stream;
+  CUDA_TRY(cudaMemcpyAsync(b.q, in->q, sizeof(double) * B * p.nq, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(b.v, in->v, sizeof(double) * B * p.nv, cudaMemcpyHostToDevice, s));
+  io.q = b.q;
+  io.v = b.v;
+  io.desired = nullptr;
+  io.cweight = io.cmaxnf = nullptr;
+  if (in->desired) {
+    const long long cnt = dstride ? drows * dstride : p.ndes;
+    CUDA_TRY(cudaMemcpyAsync(b.desired, in->desired, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+    io.desired = b.desired;
+  }
+  if (in->contact_weight) {
+    const long long cnt = cstride ? crows * cstride : p.ncontacts;
+    CUDA_TRY(cudaMemcpyAsync(b.cw, in->contact_weight, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b.cm, in->contact_maxnormalforce, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+    io.cweight = b.cw;
+    io.cmaxnf = b.cm;
+  }
+  rc = run_tick(c, B, io, b.tau, b.vdot, b.wrench, b.status, b.iters, b.res, nullptr, s);
+  if (rc) return rc;
+  if (out->tau) CUDA_TRY(cudaMemcpyAsync(out->tau, b.tau, sizeof(double) * B * p.nv, cudaMemcpyDeviceToHost, s));
+  if (out->vdot) CUDA_TRY(cudaMemcpyAsync(out->vdot, b.vdot, sizeof(double) * B * p.nv, cudaMemcpyDeviceToHost, s));
+  if (out->wrench)
+    CUDA_TRY(cudaMemcpyAsync(out->wrench, b.wrench, sizeof(double) * B * p.ncontacts * 6, cudaMemcpyDeviceToHost, s));
+  if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, b.status, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+  if (out->iters) CUDA_TRY(cudaMemcpyAsync(out->iters, b.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+  if (out->residuals)
+    CUDA_TRY(cudaMemcpyAsync(out->residuals, b.res, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, s));
+  if (out->factorizations)
+    CUDA_TRY(cudaMemcpyAsync(out->factorizations, c->be.d_nfac, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return QPC_OK;
+}
+
+int qpc_set_profiling(qpc_controller* c, int32_t on) {
+  if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
+  CUDA_TRY(cudaSetDevice(c->be.device));
+  if (on && !c->be.ev[0])
+    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&c->be.ev[i]));
+  c->be.profiling = on != 0;
+  return QPC_OK;
+}
+
+int qpc_stage_times(qpc_controller* c, double ms[3]) {
+  if (!c || !c->finalized || !c->be.ev[0]) return qpc_fail(QPC_ERR_STATE, "profiling was not enabled");
+  CUDA_TRY(cudaSetDevice(c->be.device));
+  CUDA_TRY(cudaEventSynchronize(c->be.ev[3]));
+  for (int i = 0; i < 3; i++) {
+    float t = 0;
+    CUDA_TRY(cudaEventElapsedTime(&t, c->be.ev[i], c->be.ev[i + 1]));
+    ms[i] = t;
+  }
+  return QPC_OK;
+}
+
+// ---- fp64 FMA peak of the device (the roofline denominator MEASURED_PEAKS.json does not carry) ----------------------
+__global__ void qpc_dfma_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int qpc_measure_fp64_peak(int32_t device, double* tflops) {
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CUDA_TRY(cudaEventRecord(e0));
+    qpc_dfma_peak_kernel<<<blocks, threads>>>(d, iters);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return QPC_OK;
+}
+
+int qpc_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, double* P, double* qv, double* G,
+                       double* lg, double* ug, double* lb, double* ub, double* desired_out, int32_t flags,
+                       void* stream_) {
+  if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
+  if (!in || !in->q || !in->v || B <= 0) return qpc_fail(QPC_ERR_ARG, "qpc_assemble_batch: bad arguments");
+  const DevProgram& p = c->prog;
+  std::lock_guard<std::mutex> lock(c->be.mu);
+  CUDA_TRY(cudaSetDevice(c->be.device));
+  if (c->be.dirty) {
+    int rc = upload_program(c);
+    if (rc) return rc;
+  }
+  const long long dstride = in->desired ? in->desired_stride : 0, cstride = in->contact_weight ? in->contact_stride : 0;
+  int rc = ensure_capacity(c, B, in->desired ? (dstride ? dstride : p.ndes) : 0,
+                           in->contact_weight ? (cstride ? cstride : p.ncontacts) : 0);
+  if (rc) return rc;
+  DeviceBuffers& b = c->be.buf;
+  const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
+  BatchIO io;
+  io.desired_stride = dstride;
+  io.contact_stride = cstride;
+  const DevProgram* dp = (const DevProgram*)c->be.d_prog;
+  if (flags == QPC_DEVICE_PTRS) {
+    cudaStream_t s = (cudaStream_t)stream_;
+    io.q = in->q;
+    io.v = in->v;
+    io.desired = in->desired;
+    io.cweight = in->contact_weight;
+    io.cmaxnf = in->contact_maxnormalforce;
+    QpBuffers qb = qp_view(b);
+    qb.P = P;
+    qb.qv = qv;
+    qb.G = G;
+    qb.lg = lg;
+    qb.ug = ug;
+    qb.lb = lb;
+    qb.ub = ub;
+    if (desired_out) qb.des = desired_out;
+    qpc_assemble_kernel<<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qb, B);
+    c->be.launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return QPC_OK;
+  }
+  cudaStream_t s = c->be.stream;
+  CUDA_TRY(cudaMemcpyAsync(b.q, in->q, sizeof(double) * B * p.nq, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(b.v, in->v, sizeof(double) * B * p.nv, cudaMemcpyHostToDevice, s));
+  io.q = b.q;
+  io.v = b.v;
+  io.desired = nullptr;
+  io.cweight = io.cmaxnf = nullptr;
+  if (in->desired) {
+    const long long cnt = dstride ? B * dstride : p.ndes;
+    CUDA_TRY(cudaMemcpyAsync(b.desired, in->desired, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+    io.desired = b.desired;
+  }
+  if (in->contact_weight) {
+    const long long cnt = cstride ? B * cstride : p.ncontacts;
+    CUDA_TRY(cudaMemcpyAsync(b.cw, in->contact_weight, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b.cm, in->contact_maxnormalforce, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+    io.cweight = b.cw;
+    io.cmaxnf = b.cm;
+  }
+  qpc_assemble_kernel<<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qp_view(b), B);
+  c->be.launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  const long long n = p.n, mg = p.mg, nbx = p.nbx;
+  if (P) CUDA_TRY(cudaMemcpyAsync(P, b.P, sizeof(double) * B * n * n, cudaMemcpyDeviceToHost, s));
+  if (qv) CUDA_TRY(cudaMemcpyAsync(qv, b.qv, sizeof(double) * B * n, cudaMemcpyDeviceToHost, s));
+  if (G) CUDA_TRY(cudaMemcpyAsync(G, b.G, sizeof(double) * B * mg * n, cudaMemcpyDeviceToHost, s));
+  if (lg) CUDA_TRY(cudaMemcpyAsync(lg, b.lg, sizeof(double) * B * mg, cudaMemcpyDeviceToHost, s));
+  if (ug) CUDA_TRY(cudaMemcpyAsync(ug, b.ug, sizeof(double) * B * mg, cudaMemcpyDeviceToHost, s));
+  if (lb) CUDA_TRY(cudaMemcpyAsync(lb, b.lb, sizeof(double) * B * nbx, cudaMemcpyDeviceToHost, s));
+  if (ub) CUDA_TRY(cudaMemcpyAsync(ub, b.ub, sizeof(double) * B * nbx, cudaMemcpyDeviceToHost, s));
+  if (desired_out)
+    CUDA_TRY(cudaMemcpyAsync(desired_out, b.des, sizeof(double) * B * p.ndes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return QPC_OK;
+}
+
+int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t nbox, const double* P,
+                       const double* qv, const double* G, const double* lg, const double* ug, const double* lb,
+                       const double* ub, const qpc_settings* st, double* x, double* y, int32_t* status,
+                       int32_t* iters, double* residuals, int32_t flags, void* stream_) {
+  if (B <= 0 || n <= 0 || mg < 0 || nbox < 0 || nbox > n || !P || !qv || !x || !status || !st)
+    return qpc_fail(QPC_ERR_ARG, "qpc_solve_qp_batch: bad arguments");
+  Settings s;
+  qpc_copy_settings(st, s);
+  const int asmem = admm_smem_doubles(n, mg, nbox) * 8;
+  if (asmem > 227 * 1024) return qpc_fail(QPC_ERR_LIMIT, "QP does not fit the 227 KB shared memory of one CTA");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
+  QpBuffers qb;
+  memset(&qb, 0, sizeof(qb));
+  if (flags == QPC_DEVICE_PTRS) {
+    qb.P = (double*)P;
+    qb.qv = (double*)qv;
+    qb.G = (double*)G;
+    qb.lg = (double*)lg;
+    qb.ug = (double*)ug;
+    qb.lb = (double*)lb;
+    qb.ub = (double*)ub;
+    qb.x = x;
+    qb.y = y;
+    qb.status = status;
+    qb.iters = iters;
+    qb.res = residuals;
+    qpc_admm_kernel<<<launch_grid(B), ADMM_THREADS, asmem, (cudaStream_t)stream_>>>(s, qb, n, mg, nbox, B);
+    CUDA_TRY(cudaGetLastError());
+    return QPC_OK;
+  }
+  // host pointers: temporary device copies (this entry point serves the synthetic-QP sweep, not the control tick)
+  const long long m = mg + nbox;
+  std::vector<void*> tmp;
+  auto up = [&](const double* h, long long cnt, double*& d) -> cudaError_t {
+    d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, sizeof(double) * (size_t)(cnt > 0 ? cnt : 1));
+    if (e != cudaSuccess) return e;
+    tmp.push_back(d);
+    if (h && cnt > 0) e = cudaMemcpy(d, h, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice);
+    return e;
+  };
+  int rc = QPC_OK;
+  int *dstat = nullptr, *diter = nullptr;
+  do {
+    cudaError_t e;
+    if ((e = up(P, B * n * n, qb.P)) || (e = up(qv, B * n, qb.qv)) || (e = up(G, B * mg * n, qb.G)) ||
+        (e = up(lg, B * mg, qb.lg)) || (e = up(ug, B * mg, qb.ug)) || (e = up(lb, B * nbox, qb.lb)) ||
+        (e = up(ub, B * nbox, qb.ub)) || (e = up(nullptr, B * n, qb.x)) || (e = up(nullptr, B * m, qb.y)) ||
+        (e = up(nullptr, B * 2, qb.res)) || (e = cudaMalloc((void**)&dstat, sizeof(int) * B)) ||
+        (e = cudaMalloc((void**)&diter, sizeof(int) * B))) {
+      rc = qpc_fail(QPC_ERR_CUDA, cudaGetErrorString(e));
+      break;
+    }
+    qb.status = dstat;
+    qb.iters = diter;
+    qpc_admm_kernel<<<launch_grid(B), ADMM_THREADS, asmem>>>(s, qb, n, mg, nbox, B);
+    if ((e = cudaGetLastError()) || (e = cudaDeviceSynchronize()) ||
+        (e = cudaMemcpy(x, qb.x, sizeof(double) * B * n, cudaMemcpyDeviceToHost)) ||
+        (y && (e = cudaMemcpy(y, qb.y, sizeof(double) * B * m, cudaMemcpyDeviceToHost))) ||
+        (e = cudaMemcpy(status, dstat, sizeof(int) * B, cudaMemcpyDeviceToHost)) ||
+        (iters && (e = cudaMemcpy(iters, diter, sizeof(int) * B, cudaMemcpyDeviceToHost))) ||
+        (residuals && (e = cudaMemcpy(residuals, qb.res, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost)))) {
+      rc = qpc_fail(QPC_ERR_CUDA, cudaGetErrorString(e));
+      break;
+    }
+  } while (0);
+  for (void* p : tmp) cudaFree(p);
+  if (dstat) cudaFree(dstat);
+  if (diter) cudaFree(diter);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,454 @@
+// kin.cuh -- kinematics / dynamics terms of one robot instance, one instance per CTA, tree state in shared memory.
+//
+// Device-side replacement for the RigidBodyDynamics state queries the reference's Parameters evaluate once per
+// `solve!` (call sites reference src/tasks.jl:32-39,74-81,113-120,156-169,208-219,
+// src/contacts.jl:58-61, src/lowlevel/momentum.jl:168-177, src/highlevel/standing.jl:60-76): transforms to root,
+// world-frame motion subspaces, twists, bias accelerations, world / composite inertias, centre of mass, momentum,
+// momentum-rate bias, centroidal momentum matrix, contact frames.  The sweeps are level-synchronous: bodies of one
+// tree depth are processed by different threads, QPC_SYNC() between depths.
+#pragma once
+#include "qpc_common.h"
+#include "qpc_program.h"
+
+namespace qpc {
+
+struct KinSmem {
+  double *q, *v, *des, *cw, *cm;
+  double *H, *TW, *BI, *IW, *IC, *SW;  // per body: 12, 6, 6, 10, 10 ; per velocity: 6
+  double *scr;                          // nb*12 scratch (per-body momentum / Newton-Euler terms)
+  double *tot;                          // com(3) momentum(6) hb(6) Wg(6)
+  double *A;                            // 6 x nv world-frame momentum matrix
+  double *GC;                           // ncontacts * N * 6 world wrench of each unit generator
+  double *Jt, *bt;                      // 6 x nv task Jacobian scratch, 16 scalars
+};
+
+QPC_HD int kin_smem_doubles(int nb, int nq, int nv, int ndes, int nc, int N) {
+  const int na = nv > nc ? nv : nc;
+  return nq + nv + ndes + 2 * nc + nb * (12 + 6 + 6 + 10 + 10) + nv * 6 + nb * 12 + 24 + 6 * na + nc * N * 6 + 6 * nv +
+         16 + 8;
+}
+QPC_HD KinSmem kin_layout(double* b, int nb, int nq, int nv, int ndes, int nc, int N) {
+  KinSmem s;
+  s.q = b;      b += nq;
+  s.v = b;      b += nv;
+  s.des = b;    b += ndes;
+  s.cw = b;     b += nc;
+  s.cm = b;     b += nc;
+  s.H = b;      b += nb * 12;
+  s.TW = b;     b += nb * 6;
+  s.BI = b;     b += nb * 6;
+  s.IW = b;     b += nb * 10;
+  s.IC = b;     b += nb * 10;
+  s.SW = b;     b += nv * 6;
+  s.scr = b;    b += nb * 12;
+  s.tot = b;    b += 24;
+  s.A = b;      b += 6 * (nv > nc ? nv : nc);
+  s.GC = b;     b += nc * N * 6;
+  s.Jt = b;     b += 6 * nv;
+  s.bt = b;     b += 16;
+  return s;
+}
+
+QPC_DEV Xf body_to_root(const KinSmem& s, int body) { return body < 0 ? xf_identity() : xf_load(s.H + 12 * body); }
+QPC_DEV S6 body_twist(const KinSmem& s, int body) { return body < 0 ? s6_zero() : ld6(s.TW + 6 * body); }
+QPC_DEV S6 body_bias(const KinSmem& s, int body) { return body < 0 ? s6_zero() : ld6(s.BI + 6 * body); }
+
+// load the instance inputs (q, v, desireds, contact parameters) into shared memory
+QPC_DEV void kin_load(const DevProgram* __restrict__ pg, const BatchIO& io, long long inst, KinSmem& s) {
+  const int t = QPC_TID, nt = QPC_NT;
+  for (int i = t; i < pg->nq; i += nt) s.q[i] = io.q[inst * pg->nq + i];
+  for (int i = t; i < pg->nv; i += nt) s.v[i] = io.v[inst * pg->nv + i];
+  for (int i = t; i < pg->ndes; i += nt)
+    s.des[i] = io.desired ? io.desired[inst * io.desired_stride + i] : pg->def_desired[i];
+  for (int i = t; i < pg->ncontacts; i += nt) {
+    s.cw[i] = io.cweight ? io.cweight[inst * io.contact_stride + i] : pg->def_cweight[i];
+    s.cm[i] = io.cmaxnf ? io.cmaxnf[inst * io.contact_stride + i] : pg->def_cmaxnf[i];
+  }
+  QPC_SYNC();
+}
+
+// forward sweep: transform_to_root, motion subspaces, twist_wrt_world, bias_acceleration, world inertias
+QPC_DEV void kin_forward(const DevProgram* __restrict__ pg, KinSmem& s) {
+  for (int lvl = 0; lvl < pg->nlevels; lvl++) {
+    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
+      const int b = pg->level_body[k];
+      const int par = pg->parent[b];
+      const int jt = pg->jtype[b];
+      const double* qj = s.q + pg->qoff[b];
+      Xf Xj = xf_identity();
+      V3 ax = ld3(pg->axis + 3 * b);
+      if (jt == 0) {
+        axis_angle_to_rot(ax, qj[0], Xj.R);
+      } else if (jt == 1) {
+        Xj.p = qj[0] * ax;
+      } else if (jt == 2) {
+        double nn = 1.0 / sqrt(qj[0] * qj[0] + qj[1] * qj[1] + qj[2] * qj[2] + qj[3] * qj[3]);
+        quat_to_rot(qj[0] * nn, qj[1] * nn, qj[2] * nn, qj[3] * nn, Xj.R);
+        Xj.p = mk3(qj[4], qj[5], qj[6]);
+      }
+      Xf Xt;
+      for (int i = 0; i < 9; i++) Xt.R[i] = pg->XR[9 * b + i];
+      Xt.p = ld3(pg->Xp + 3 * b);
+      Xf H = xf_mul(xf_mul(body_to_root(s, par), Xt), Xj);
+      xf_store(s.H + 12 * b, H);
+      const int o = pg->voff[b];
+      S6 jtw = s6_zero();
+      if (jt == 0) {
+        S6 S = xmotion(H, mk6(ax, mk3(0, 0, 0)));
+        st6(s.SW + 6 * o, S);
+        jtw = s.v[o] * S;
+      } else if (jt == 1) {
+        S6 S = xmotion(H, mk6(mk3(0, 0, 0), ax));
+        st6(s.SW + 6 * o, S);
+        jtw = s.v[o] * S;
+      } else if (jt == 2) {
+        for (int c = 0; c < 3; c++) {
+          V3 e = mk3(c == 0, c == 1, c == 2);
+          S6 Sa = xmotion(H, mk6(e, mk3(0, 0, 0)));
+          S6 Sl = xmotion(H, mk6(mk3(0, 0, 0), e));
+          st6(s.SW + 6 * (o + c), Sa);
+          st6(s.SW + 6 * (o + 3 + c), Sl);
+          jtw = jtw + s.v[o + c] * Sa + s.v[o + 3 + c] * Sl;
+        }
+      }
+      S6 tw = body_twist(s, par) + jtw;
+      st6(s.TW + 6 * b, tw);
+      st6(s.BI + 6 * b, body_bias(s, par) + cross_motion(tw, jtw));
+      SI Iw = si_transform(H, si_load(pg->inertia + 10 * b));
+      si_store(s.IW + 10 * b, Iw);
+      // per-body momentum and Newton-Euler bias terms (summed in kin_totals)
+      st6(s.scr + 12 * b, si_mul(Iw, tw));
+      st6(s.scr + 12 * b + 6, newton_euler(Iw, ld6(s.BI + 6 * b), tw));
+    }
+    QPC_SYNC();
+  }
+}
+
+// composite rigid-body inertias (children summed into parents, deepest level first), centre of mass, momentum,
+// momentum_rate_bias, gravity wrench, world-frame momentum matrix
+QPC_DEV void kin_composite(const DevProgram* __restrict__ pg, KinSmem& s) {
+  for (int lvl = pg->nlevels - 1; lvl >= 0; lvl--) {
+    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
+      const int b = pg->level_body[k];
+      double acc[10];
+      for (int i = 0; i < 10; i++) acc[i] = s.IW[10 * b + i];
+      for (int c = pg->child_ptr[b]; c < pg->child_ptr[b + 1]; c++) {
+        const int ch = pg->child_idx[c];
+        for (int i = 0; i < 10; i++) acc[i] += s.IC[10 * ch + i];
+      }
+      for (int i = 0; i < 10; i++) s.IC[10 * b + i] = acc[i];
+    }
+    QPC_SYNC();
+  }
+  // totals: 12 sums over bodies + centre of mass from the roots' composite inertia
+  for (int c = QPC_TID; c < 12; c += QPC_NT) {
+    double a = 0;
+    for (int b = 0; b < pg->nb; b++) a += s.scr[12 * b + c];
+    s.tot[3 + c] = a;  // momentum (3..8), momentum_rate_bias (9..14)
+  }
+  for (int c = QPC_TID; c < 3; c += QPC_NT) {
+    double a = 0;
+    for (int b = 0; b < pg->nb; b++)
+      if (pg->parent[b] < 0) a += s.IC[10 * b + 6 + c];
+    s.tot[c] = a / pg->total_mass;
+  }
+  // momentum matrix column c = I^c_{succ(joint)} S_c (world frame)   (momentum_matrix!, momentum.jl:168)
+  for (int c = QPC_TID; c < pg->nv; c += QPC_NT) {
+    S6 col = si_mul(si_load(s.IC + 10 * pg->vbody[c]), ld6(s.SW + 6 * c));
+    for (int r = 0; r < 6; r++) s.A[r * pg->nv + c] = s6_get(col, r);
+  }
+  QPC_SYNC();
+  if (QPC_TID == 0) {
+    V3 fg = pg->total_mass * ld3(pg->gravity);
+    st6(s.tot + 15, mk6(cross(ld3(s.tot), fg), fg));  // Wg = (c x m g, m g)  (momentum.jl:170)
+  }
+  QPC_SYNC();
+}
+
+// StandingController PD laws (standing.jl:60-85) -> desireds of the tasks it owns
+QPC_DEV void kin_standing(const DevProgram* __restrict__ pg, KinSmem& s) {
+  if (!pg->standing) return;
+  const double mass = pg->total_mass;
+  for (int k = QPC_TID; k < pg->st_nj + 2; k += QPC_NT) {
+    if (k == pg->st_nj) {  // centre of mass: m * (-k (c - cref) - d hlin / m)
+      for (int c = 0; c < 3; c++) {
+        double e = s.tot[c] - pg->st_comref[c];
+        double ed = s.tot[3 + 3 + c] / mass;
+        s.des[pg->st_linmom_des + c] = mass * (-pg->st_com_kp * e - pg->st_com_kd * ed);
+      }
+    } else if (k == pg->st_nj + 1) {  // pelvis orientation: -k rotvec(R) - d omega_body
+      Xf H = body_to_root(s, pg->st_pelvis_body);
+      S6 T = xmotion(xf_inv(H), body_twist(s, pg->st_pelvis_body));
+      V3 rv = rot_to_rotvec(H.R);
+      V3 wd = (-pg->st_pelvis_kp) * rv + (-pg->st_pelvis_kd) * T.w;
+      st3(s.des + pg->st_pelvis_des, wd);
+    } else {
+      s.des[pg->st_jdes[k]] = -pg->st_kp[k] * (s.q[pg->st_jq[k]] - pg->st_ref[k]) - pg->st_kd[k] * s.v[pg->st_jv[k]];
+    }
+  }
+  QPC_SYNC();
+}
+
+// contact frames and unit-generator wrenches: toroot = transform_to_root(body) * z_up (contacts.jl:61);
+// generator g of contact c produces the world wrench (p x (R b_g); R b_g)  (contacts.jl:63,66,67)
+QPC_DEV void kin_contacts(const DevProgram* __restrict__ pg, KinSmem& s) {
+  const int N = pg->N;
+  for (int k = QPC_TID; k < pg->ncontacts * N; k += QPC_NT) {
+    const int c = k / N, g = k % N;
+    const DevContact& dc = pg->contacts[c];
+    Xf Z;
+    for (int i = 0; i < 9; i++) Z.R[i] = dc.Rz[i];
+    Z.p = ld3(dc.pos);
+    Xf T = xf_mul(body_to_root(s, dc.body), Z);
+    V3 f = rot(T.R, mk3(dc.B[g], dc.B[N + g], dc.B[2 * N + g]));
+    st6(s.GC + 6 * k, mk6(cross(T.p, f), f));
+  }
+  QPC_SYNC();
+}
+
+// rows of task_error = J vd + b - desired for one task into s.Jt (dim x nv) and s.bt (dim)
+// (tasks.jl:31-44,73-84,112-123,153-171,185-189,230-236,258-262)
+QPC_DEV void kin_task_rows(const DevProgram* __restrict__ pg, KinSmem& s, const DevTask& t) {
+  const int nv = pg->nv;
+  for (int i = QPC_TID; i < 6 * nv; i += QPC_NT) s.Jt[i] = 0.0;
+  QPC_SYNC();
+  const int kind = t.kind;
+  if (kind <= 3) {  // path tasks: geometric Jacobian in `frame` (point task: the base frame)
+    const Xf Xinv = xf_inv(body_to_root(s, t.frame));
+    V3 p = mk3(0, 0, 0);
+    if (kind == 3) {
+      Xf rel = xf_mul(Xinv, body_to_root(s, t.target));
+      p = rot(rel.R, ld3(t.point)) + rel.p;
+    }
+    const int r0 = kind == 2 ? 3 : 0;
+    for (int e = QPC_TID; e < t.path_len; e += QPC_NT) {
+      const int b = pg->path_body[t.path_ptr + e];
+      const double sgn = (double)pg->path_sign[t.path_ptr + e];
+      for (int c = pg->voff[b]; c < pg->voff[b] + pg->nvj[b]; c++) {
+        S6 col = sgn * xmotion(Xinv, ld6(s.SW + 6 * c));
+        if (kind == 3) {
+          V3 pj = cross(col.w, p) + col.v;  // point_jacobian!: J_lin + J_ang x p
+          s.Jt[0 * nv + c] = pj.x;
+          s.Jt[1 * nv + c] = pj.y;
+          s.Jt[2 * nv + c] = pj.z;
+        } else {
+          for (int r = 0; r < t.dim; r++) s.Jt[r * nv + c] = s6_get(col, r0 + r);
+        }
+      }
+    }
+    if (QPC_TID == 0) {
+      // transform(state, -bias(source) + bias(target), frame): X [ a + (-T_frame) x (T_target - T_source) ]
+      S6 rel = body_twist(s, t.target) - body_twist(s, t.source);
+      S6 a = body_bias(s, t.target) - body_bias(s, t.source);
+      S6 neg = (-1.0) * body_twist(s, t.frame);
+      S6 jv = xmotion(Xinv, a + cross_motion(neg, rel));
+      if (kind == 3) {
+        S6 T = xmotion(Xinv, rel);
+        V3 pd = cross(T.w, p) + T.v;
+        V3 bb = cross(T.w, pd) + cross(jv.w, p) + jv.v;
+        st3(s.bt, bb);
+      } else {
+        for (int r = 0; r < t.dim; r++) s.bt[r] = s6_get(jv, r0 + r);
+      }
+    }
+  } else if (kind == 4) {
+    for (int r = QPC_TID; r < t.dim; r += QPC_NT) {
+      s.Jt[r * nv + pg->voff[t.joint] + r] = 1.0;
+      s.bt[r] = 0.0;
+    }
+  } else {  // momentum-rate tasks: force-transform of the world momentum matrix to the centroidal frame
+    const V3 com = ld3(s.tot);
+    const int r0 = kind == 6 ? 3 : 0;
+    for (int c = QPC_TID; c < nv; c += QPC_NT) {
+      V3 aw = mk3(s.A[0 * nv + c], s.A[1 * nv + c], s.A[2 * nv + c]);
+      V3 al = mk3(s.A[3 * nv + c], s.A[4 * nv + c], s.A[5 * nv + c]);
+      S6 col = mk6(aw - cross(com, al), al);
+      for (int r = 0; r < t.dim; r++) s.Jt[r * nv + c] = s6_get(col, r0 + r);
+    }
+    if (QPC_TID == 0) {
+      S6 hb = ld6(s.tot + 9);
+      S6 hc = mk6(hb.w - cross(com, hb.v), hb.v);
+      for (int r = 0; r < t.dim; r++) s.bt[r] = s6_get(hc, r0 + r);
+    }
+  }
+  QPC_SYNC();
+}
+
+// ---- QP assembly (condensed form) ------------------------------------------------------------------
+// x = (free vd, rho);  P = 2 sum J'WJ + 2 reg (+ 2 w_c B'B on the rho blocks), q = 2 sum J'W r;
+// general rows: hard tasks J x = -r, wrench balance S'(A vd - sum G_c rho_c) = S'(Wg - Adot v); box 0 <= rho <= maxrho.
+// r = b - desired + J_fixed vd_fixed accounts for velocities fixed by hard JointAccelerationTasks.
+// P, qv, G, lg, ug, lb, ub point at this instance's slots (global or shared memory).
+QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double* P, double* qv, double* G, double* lg,
+                          double* ug, double* lb, double* ub) {
+  const int n = pg->n, nv = pg->nv, mg = pg->mg, N = pg->N, nvf = pg->nvf;
+  const int t0 = QPC_TID, nt = QPC_NT;
+  for (int i = t0; i < n * n; i += nt) P[i] = 0.0;
+  for (int i = t0; i < mg * n; i += nt) G[i] = 0.0;
+  for (int i = t0; i < n; i += nt) qv[i] = 0.0;
+  QPC_SYNC();
+  // regularisation and contact-force cost
+  for (int i = t0; i < nv; i += nt)
+    if (pg->vcol[i] >= 0) P[pg->vcol[i] * n + pg->vcol[i]] = 2.0 * pg->reg[i];
+  for (int k = t0; k < pg->ncontacts * N * N; k += nt) {
+    const int c = k / (N * N), a = (k / N) % N, b = k % N;
+    const DevContact& dc = pg->contacts[c];
+    P[(dc.col0 + a) * n + dc.col0 + b] = 2.0 * s.cw[c] * dc.BtB[a * N + b];
+  }
+  for (int k = t0; k < pg->ncontacts * N; k += nt) {
+    const int c = k / N;
+    lb[k] = 0.0;
+    ub[k] = s.cm[c] * pg->contacts[c].maxrho_factor;
+  }
+  QPC_SYNC();
+  for (int ti = 0; ti < pg->ntasks; ti++) {
+    const DevTask& t = pg->tasks[ti];
+    if (t.eliminated) continue;
+    kin_task_rows(pg, s, t);
+    double* r = s.bt + 8;
+    for (int k = t0; k < t.dim; k += nt) {
+      double a = s.bt[k] - s.des[t.des_off + k];
+      for (int i = 0; i < nv; i++)
+        if (pg->vcol[i] < 0) a += s.Jt[k * nv + i] * s.des[pg->vfix_des[i]];
+      r[k] = a;
+    }
+    QPC_SYNC();
+    if (t.mode == 0) {
+      for (int k = t0; k < t.dim * nv; k += nt) {
+        const int row = k / nv, i = k % nv;
+        if (pg->vcol[i] >= 0) G[(t.row0 + row) * n + pg->vcol[i]] = s.Jt[k];
+      }
+      for (int k = t0; k < t.dim; k += nt) lg[t.row0 + k] = ug[t.row0 + k] = -r[k];
+    } else {
+      // P_vv += 2 J'WJ, q_v += 2 J'W r
+      const double* W = pg->Wbuf + t.w_off;
+      for (int k = t0; k < nv * nv; k += nt) {
+        const int i = k / nv, j = k % nv;
+        const int ci = pg->vcol[i], cj = pg->vcol[j];
+        if (ci < 0 || cj < 0) continue;
+        double a = 0;
+        if (t.mode == 1) {
+          for (int rr = 0; rr < t.dim; rr++) a += s.Jt[rr * nv + i] * s.Jt[rr * nv + j];
+          a *= t.weight;
+        } else {
+          for (int rr = 0; rr < t.dim; rr++)
+            for (int ss = 0; ss < t.dim; ss++)
+              a += 0.5 * s.Jt[rr * nv + i] * (W[rr * t.dim + ss] + W[ss * t.dim + rr]) * s.Jt[ss * nv + j];
+        }
+        P[ci * n + cj] += 2.0 * a;
+      }
+      for (int i = t0; i < nv; i += nt) {
+        const int ci = pg->vcol[i];
+        if (ci < 0) continue;
+        double a = 0;
+        if (t.mode == 1) {
+          for (int rr = 0; rr < t.dim; rr++) a += s.Jt[rr * nv + i] * r[rr];
+          a *= t.weight;
+        } else {
+          // x'Wx with a possibly unsymmetric W: gradient uses (W + W')/2
+          for (int rr = 0; rr < t.dim; rr++)
+            for (int ss = 0; ss < t.dim; ss++)
+              a += 0.5 * s.Jt[rr * nv + i] * (W[rr * t.dim + ss] + W[ss * t.dim + rr]) * r[ss];
+        }
+        qv[ci] += 2.0 * a;
+      }
+    }
+    QPC_SYNC();
+  }
+  if (pg->floating >= 0) {  // add_wrench_balance_constraint! (momentum.jl:162-193)
+    const int o = pg->voff[pg->floating], row0 = pg->balance_row0;
+    // SA = S'A (6 x nv) into Jt
+    for (int k = t0; k < 6 * nv; k += nt) {
+      const int kk = k / nv, c = k % nv;
+      S6 S = ld6(s.SW + 6 * (o + kk));
+      s.Jt[k] = S.w.x * s.A[c] + S.w.y * s.A[nv + c] + S.w.z * s.A[2 * nv + c] + S.v.x * s.A[3 * nv + c] +
+                S.v.y * s.A[4 * nv + c] + S.v.z * s.A[5 * nv + c];
+    }
+    QPC_SYNC();
+    for (int k = t0; k < 6 * nv; k += nt) {
+      const int kk = k / nv, i = k % nv;
+      if (pg->vcol[i] >= 0) G[(row0 + kk) * n + pg->vcol[i]] = s.Jt[k];
+    }
+    for (int k = t0; k < 6 * pg->ncontacts * N; k += nt) {
+      const int kk = k / (pg->ncontacts * N), cg = k % (pg->ncontacts * N);
+      G[(row0 + kk) * n + nvf + cg] = -dot(ld6(s.SW + 6 * (o + kk)), ld6(s.GC + 6 * cg));
+    }
+    for (int kk = t0; kk < 6; kk += nt) {
+      double a = dot(ld6(s.SW + 6 * (o + kk)), ld6(s.tot + 15) - ld6(s.tot + 9));
+      for (int i = 0; i < nv; i++)
+        if (pg->vcol[i] < 0) a -= s.Jt[kk * nv + i] * s.des[pg->vfix_des[i]];
+      lg[row0 + kk] = ug[row0 + kk] = a;
+    }
+    QPC_SYNC();
+  }
+  // symmetrise P against summation-order noise: not needed, the accumulation above is symmetric by construction
+}
+
+// ---- epilogue: contact wrenches, inverse dynamics (momentum.jl:62-80) ------------------------------------------------
+// x = condensed solution.  Writes vd (nv), per-contact world wrenches (nc x 6) and tau (nv) to the given slots.
+QPC_DEV void kin_inverse_dynamics(const DevProgram* __restrict__ pg, KinSmem& s, const double* x, double* vd_out,
+                                  double* wrench_out, double* tau_out) {
+  const int nv = pg->nv, nb = pg->nb, N = pg->N, nvf = pg->nvf;
+  double* vd = s.Jt;            // nv
+  double* ext = s.scr;          // nb * 6 external wrench per body (then joint wrenches)
+  double* acc = s.scr + 6 * nb; // nb * 6 spatial accelerations
+  for (int i = QPC_TID; i < nv; i += QPC_NT) {
+    const int ci = pg->vcol[i];
+    vd[i] = ci >= 0 ? x[ci] : s.des[pg->vfix_des[i]];
+    if (vd_out) vd_out[i] = vd[i];
+  }
+  for (int i = QPC_TID; i < 6 * nb; i += QPC_NT) ext[i] = 0.0;
+  QPC_SYNC();
+  // value(model, point.wrench_world) = sum_g rho_g * generator wrench; summed per body (momentum.jl:65-72)
+  for (int k = QPC_TID; k < pg->ncontacts * 6; k += QPC_NT) {
+    const int c = k / 6, r = k % 6;
+    double a = 0;
+    for (int g = 0; g < N; g++) a += x[nvf + c * N + g] * s.GC[6 * (c * N + g) + r];
+    if (wrench_out) wrench_out[k] = a;
+    s.A[k] = a;  // A is free now: stash per-contact wrenches
+  }
+  QPC_SYNC();
+  for (int k = QPC_TID; k < nb * 6; k += QPC_NT) {
+    const int b = k / 6, r = k % 6;
+    double a = 0;
+    for (int c = 0; c < pg->ncontacts; c++)
+      if (pg->contacts[c].body == b) a += s.A[6 * c + r];
+    ext[k] = a;
+  }
+  QPC_SYNC();
+  // forward: spatial accelerations with gravity as root acceleration, joint wrench = I a + T x* I T - ext
+  for (int lvl = 0; lvl < pg->nlevels; lvl++) {
+    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
+      const int b = pg->level_body[k], par = pg->parent[b];
+      S6 a = par < 0 ? mk6(mk3(0, 0, 0), -ld3(pg->gravity)) : ld6(acc + 6 * par);
+      for (int c = pg->voff[b]; c < pg->voff[b] + pg->nvj[b]; c++) a = a + vd[c] * ld6(s.SW + 6 * c);
+      a = a + (body_bias(s, b) - body_bias(s, par));
+      st6(acc + 6 * b, a);
+    }
+    QPC_SYNC();
+  }
+  for (int b = QPC_TID; b < nb; b += QPC_NT) {
+    S6 w = newton_euler(si_load(s.IW + 10 * b), ld6(acc + 6 * b), ld6(s.TW + 6 * b)) - ld6(ext + 6 * b);
+    st6(ext + 6 * b, w);
+  }
+  QPC_SYNC();
+  // backward: parents accumulate their children's wrenches, deepest level first
+  for (int lvl = pg->nlevels - 2; lvl >= 0; lvl--) {
+    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
+      const int b = pg->level_body[k];
+      S6 w = ld6(ext + 6 * b);
+      for (int c = pg->child_ptr[b]; c < pg->child_ptr[b + 1]; c++) w = w + ld6(ext + 6 * pg->child_idx[c]);
+      st6(ext + 6 * b, w);
+    }
+    QPC_SYNC();
+  }
+  for (int c = QPC_TID; c < nv; c += QPC_NT) {
+    const int b = pg->vbody[c];
+    double tau = dot(ld6(s.SW + 6 * c), ld6(ext + 6 * b));
+    if (b == pg->floating) tau = 0.0;  // zero_floating_joint_torques! (momentum.jl:93-97)
+    tau_out[c] = tau;
+  }
+  QPC_SYNC();
+}
+
+}  // namespace qpc

@@ -1,0 +1,90 @@
+// qpc_program.h -- the static "controller program": flat device tables compiled once from the setup-time API calls
+// (MomentumBasedController / addtask! / addcontact! / regularize! / StandingController, reference
+// src/lowlevel/momentum.jl:15-33,99-148 and src/highlevel/standing.jl:18-56).  One copy lives in global memory per
+// device and is read by every CTA.
+#pragma once
+#include <stdint.h>
+
+#define QPC_MAXB 48     // bodies
+#define QPC_MAXV 64     // velocity dimension
+#define QPC_MAXQ 72     // configuration dimension
+#define QPC_MAXT 64     // tasks
+#define QPC_MAXC 16     // contact points
+#define QPC_MAXN 8      // friction-cone generators per contact
+#define QPC_MAXPATH 512 // total path entries over all tasks
+#define QPC_MAXDES 160  // total desired dimension
+#define QPC_MAXW 256    // matrix-weight storage (doubles)
+
+namespace qpc {
+
+struct Settings {
+  double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
+  int max_iter, scaling, adaptive_rho, adaptive_rho_interval, check_termination;
+};
+
+struct DevTask {
+  int kind, mode, dim, source, target, frame, joint, des_off;
+  int row0;                // first row in G (hard, not eliminated) or -1
+  int path_ptr, path_len;  // entries of path_body / path_sign
+  int w_off;               // matrix weight offset in Wbuf
+  int eliminated;          // hard joint task: its velocities are substituted, no rows
+  double weight;
+  double point[3];
+};
+
+struct DevContact {
+  int body, col0;       // first rho column in x
+  double Rz[9], pos[3]; // z_up_transform(position, normal)  (contacts.jl:8-14)
+  double B[3 * QPC_MAXN];          // forcebasis(mu, N), 3 x N row-major (contacts.jl:16-23)
+  double BtB[QPC_MAXN * QPC_MAXN]; // B'B
+  double maxrho_factor;            // 1 / (N sqrt(mu^2 + 1))  (contacts.jl:57)
+};
+
+struct DevProgram {
+  // ---- mechanism -------------------------------------------------------------------------------------------
+  int nb, nq, nv;
+  int parent[QPC_MAXB], jtype[QPC_MAXB], qoff[QPC_MAXB], voff[QPC_MAXB], nvj[QPC_MAXB];
+  int vbody[QPC_MAXV];
+  int nlevels, level_ptr[QPC_MAXB + 1], level_body[QPC_MAXB];  // bodies grouped by depth
+  int child_ptr[QPC_MAXB + 1], child_idx[QPC_MAXB];
+  double axis[QPC_MAXB * 3], XR[QPC_MAXB * 9], Xp[QPC_MAXB * 3];
+  double inertia[QPC_MAXB * 10];  // body-frame SI (see qpc_common.h)
+  double gravity[3], total_mass;
+  // ---- program ---------------------------------------------------------------------------------------------
+  int N, floating;  // floating = successor body of the floating joint or -1
+  int ntasks, ncontacts, ndes;
+  int n, nvf, mg, nbx;  // condensed QP: n = nvf + ncontacts*N variables, mg general rows, nbx box rows (the rhos)
+  int balance_row0;
+  int vcol[QPC_MAXV];      // column of velocity i in x, or -1 when fixed by a hard JointAccelerationTask
+  int vfix_des[QPC_MAXV];  // desired offset providing the value of a fixed velocity
+  double reg[QPC_MAXV];
+  DevTask tasks[QPC_MAXT];
+  int path_body[QPC_MAXPATH], path_sign[QPC_MAXPATH];
+  double Wbuf[QPC_MAXW];
+  DevContact contacts[QPC_MAXC];
+  double def_desired[QPC_MAXDES], def_cweight[QPC_MAXC], def_cmaxnf[QPC_MAXC];
+  // ---- StandingController constants (standing.jl:1-16) ---------------------------------------------------------
+  int standing, st_linmom_des, st_pelvis_des, st_pelvis_body, st_nj;
+  int st_jq[QPC_MAXV], st_jv[QPC_MAXV], st_jdes[QPC_MAXV];
+  double st_kp[QPC_MAXV], st_kd[QPC_MAXV], st_ref[QPC_MAXV];
+  double st_com_kp, st_com_kd, st_pelvis_kp, st_pelvis_kd, st_comref[3];
+  Settings settings;
+};
+
+// per-batch I/O of the tick (device pointers)
+struct BatchIO {
+  const double *q, *v, *desired, *cweight, *cmaxnf;
+  long long desired_stride, contact_stride;
+};
+
+// the condensed QP of every instance, as written by the assembly kernel and consumed by the ADMM kernel
+struct QpBuffers {
+  double *P, *qv, *G, *lg, *ug, *lb, *ub;  // [B][n*n], [B][n], [B][mg*n], [B][mg], [B][mg], [B][nbx], [B][nbx]
+  double* des;                              // [B][ndes] desireds actually used (standing laws applied)
+  double *x, *y;                            // [B][n], [B][mg+nbx]
+  int *status, *iters;
+  double* res;  // [B][2]
+  int* nfac;    // [B] number of factorisations (1 + rho updates), optional
+};
+
+}  // namespace qpc

@@ -1,0 +1,198 @@
+"""CPU-only: the CUDA kernel bodies (csrc/kin.cuh, csrc/admm.cuh), compiled single-threaded by tests/emu, against the
+oracle.  Catches arithmetic errors before GPU minutes are spent; the GPU tests repeat these through the C ABI."""
+import numpy as np
+import pytest
+
+import parity
+from emu import emu
+from qpcontrol_jl_b200 import (JointAccelerationTask, MomentumBasedController, MomentumRateTask, OSQPSettings,
+                               PointAccelerationTask, SpatialAccelerationTask, scenarios)
+from qpcontrol_jl_b200.mechanism import PRISMATIC, REVOLUTE, rand_floating_humanoid, rand_tree
+
+
+def test_atlas_standing_tick(orc):
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    q, v = scenarios.atlas_random_states(mech, qnom, 24, seed=3)
+    res = emu.EmuController(low.program).solve(q, v)
+    ref = orc.OracleController(low.program).solve_batch(q, v)
+    assert np.all(res.status == 1)
+    parity.assert_tick_parity(res, ref, low.program)
+    assert np.all(res.tau[:, :6] == 0.0)
+    assert (low.finalize if False else True)
+    h = emu.EmuController(low.program).h
+    assert (h.n, h.mg, h.nbox) == (50, 21, 32)  # 18 free vd + 32 rho; feet 12 + pelvis 3 + balance 6
+
+
+def test_atlas_contact_masks(orc):
+    """config 4: per-instance active contact sets; disabled contacts must carry exactly zero wrench."""
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    B = 24
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=4)
+    cm = scenarios.contact_masks(B, 8, seed=4)
+    cw = np.full((B, 8), 1e-3)
+    res = emu.EmuController(low.program).solve(q, v, None, cw, cm)
+    ref = orc.OracleController(low.program).solve_batch(q, v, cweight=cw, cmaxnf=cm)
+    parity.assert_tick_parity(res, ref, low.program)
+    ok = (res.status == 1) | (res.status == 2)
+    off = (cm == 0)[ok]
+    assert np.abs(res.wrenches[ok][off]).max(initial=0) < 1e-6
+
+
+def test_condensed_qp_matches_lifted_solution(orc):
+    """The oracle's lifted solution satisfies the condensed constraints and is stationary for the condensed cost."""
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    q, v = scenarios.atlas_random_states(mech, qnom, 3, seed=8)
+    oc = orc.OracleController(low.program)
+    a = emu.EmuController(low.program).assemble(q, v)
+    o = oc.solve_batch(q, v, return_lifted=True)
+    pr = low.program
+    fixed = np.zeros(mech.nv, bool)
+    for e in pr.tasks:
+        if isinstance(e.task, JointAccelerationTask) and e.mode == 0:
+            fixed[list(mech.velocity_range(e.task.joint))] = True
+    for i in range(3):
+        xl = o["x_lifted"][i]
+        x = np.concatenate([o["vd"][i][~fixed]] + [xl[36 + 13 * c:36 + 13 * c + 4] for c in range(8)])
+        np.testing.assert_allclose(a["G"][i] @ x, a["lg"][i], atol=1e-6)
+        assert np.array_equal(a["lg"][i], a["ug"][i])
+        assert np.all(x[18:] >= -1e-7) and np.all(x[18:] <= a["ub"][i] + 1e-7)
+        P = a["P"][i]
+        np.testing.assert_allclose(P, P.T, atol=1e-12)
+        # stationarity on the free (inactive-bound) coordinates, projected on the null space of G
+        g = P @ x + a["q"][i]
+        act = x[18:] < 1e-7
+        free = np.concatenate([np.ones(18, bool), ~act])
+        Gf = a["G"][i][:, free]
+        y, *_ = np.linalg.lstsq(Gf.T, -g[free], rcond=None)
+        assert np.abs(g[free] + Gf.T @ y).max() < 1e-5 * max(1.0, np.abs(g).max())
+
+
+@pytest.mark.parametrize("constrained", [True, False])
+def test_fixed_base_joint_space(orc, constrained):
+    rng = np.random.default_rng(42)
+    mech = rand_tree(rng, [PRISMATIC, REVOLUTE, REVOLUTE])
+    ctrl = MomentumBasedController(mech, OSQPSettings.test_suite())
+    for j in range(mech.nb):
+        t = JointAccelerationTask(mech, j)
+        ctrl.addtask(t) if constrained else ctrl.addtask(t, 1.0)
+        t.setdesired(rng.random(1))
+    q = np.stack([mech.rand_configuration(rng) for _ in range(5)])
+    v = rng.standard_normal((5, mech.nv))
+    res = emu.EmuController(ctrl.program).solve(q, v)
+    ref = orc.OracleController(ctrl.program).solve_batch(q, v)
+    parity.assert_tick_parity(res, ref, ctrl.program)
+
+
+@pytest.mark.parametrize("mode", ["constraint", "scalar", "matrix"])
+def test_spatial_acceleration_modes(orc, mode):
+    rng = np.random.default_rng(533)
+    mech = rand_floating_humanoid(rng)
+    ctrl = MomentumBasedController(mech, OSQPSettings.test_suite(), floatingjoint=0)
+    body, base = mech.findbody("l_foot"), mech.findbody("r_hand")
+    task = SpatialAccelerationTask(mech, base, body, frame=base)
+    if mode == "constraint":
+        ctrl.addtask(task)
+        for j in range(mech.nb):
+            ctrl.regularize(j, 1.0)
+    elif mode == "scalar":
+        ctrl.addtask(task, 1.0)
+    else:
+        W = rng.random((6, 6))
+        ctrl.addtask(task, W @ W.T + np.eye(6))
+    task.setdesired(rng.random(6))
+    q = np.stack([mech.rand_configuration(rng) for _ in range(3)])
+    v = rng.standard_normal((3, mech.nv))
+    res = emu.EmuController(ctrl.program).solve(q, v)
+    ref = orc.OracleController(ctrl.program).solve_batch(q, v)
+    assert np.all(res.status == 1)
+    if mode == "constraint":
+        parity.assert_tick_parity(res, ref, ctrl.program)
+    else:
+        # without regularisation vd is not unique (P is singular): compare the achieved task acceleration instead
+        st = orc.OracleState(orc.OracleMechanism(mech))
+        for i in range(3):
+            st.set(q[i], v[i])
+            J, b = st.geometric_jacobian(base, body, base), st.bias_in_frame(base, body, base)
+            np.testing.assert_allclose(J @ res.vdot[i] + b, task.desired, atol=1e-6)
+
+
+def test_momentum_rate_task_with_random_contacts(orc):
+    rng = np.random.default_rng(533454)
+    mech = rand_floating_humanoid(rng)
+    ctrl = MomentumBasedController(mech, OSQPSettings.test_suite(), floatingjoint=0)
+    pts = []
+    for body in range(mech.nb):
+        for pos in mech.contact_points.get(body, ()):
+            n = rng.standard_normal(3)
+            c = ctrl.addcontact(body, pos, n / np.linalg.norm(n), float(rng.uniform(0.3, 1.0)))
+            c.weight, c.maxnormalforce = 1e-6, 1e9
+            pts.append(c)
+    task = MomentumRateTask(mech)
+    ctrl.addtask(task)
+    for j in range(mech.nb):
+        ctrl.regularize(j, 1e-6)
+    q = np.stack([mech.rand_configuration(rng) for _ in range(4)])
+    v = rng.standard_normal((4, mech.nv))
+    # an achievable momentum rate: gravity + small in-cone forces is what the reference test builds; here simply
+    # ask for the gravity wrench (free fall is always achievable) and compare with the oracle
+    task.setdesired(np.concatenate([np.zeros(3), mech.total_mass * mech.gravity]))
+    res = emu.EmuController(ctrl.program).solve(q, v)
+    ref = orc.OracleController(ctrl.program).solve_batch(q, v)
+    assert np.all((res.status == 1) | (res.status == 2))
+    ok = (ref["status"] == 1) | (ref["status"] == 2)
+    assert parity.rel_err(res.tau[ok], ref["tau"][ok]).max() < 1e-4
+
+
+def test_acrobot_point_task(orc):
+    mech, low, task = scenarios.acrobot_point_task()
+    q, v, des = scenarios.acrobot_random_inputs(mech, 64, seed=2)
+    res = emu.EmuController(low.program).solve(q, v, des)
+    ref = orc.OracleController(low.program).solve_batch(q, v, desired=des)
+    parity.assert_tick_parity(res, ref, low.program)
+    # the notebook's PD law in scenarios.acrobot_random_inputs uses planar forward kinematics: check it against the
+    # oracle's transform of the task point
+    st = orc.OracleState(orc.OracleMechanism(mech)).set(q[0], v[0])
+    R, p = st.transform_to_root(1)
+    tip = R @ np.array(scenarios.ACROBOT_POINT) + p
+    a1, a2 = q[0, 0], q[0, 0] + q[0, 1]
+    np.testing.assert_allclose(tip, [-np.sin(a1) - 2.05 * np.sin(a2), 0.25, -np.cos(a1) - 2.05 * np.cos(a2)], atol=1e-12)
+
+
+@pytest.mark.parametrize("n,m", [(30, 30), (68, 71)])
+def test_dense_qp(orc, n, m):
+    P, qv, A, l, u = scenarios.synthetic_qps(6, n, m, seed=5)
+    st = OSQPSettings(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000)
+    res = emu.solve_qp_batch(P, qv, A, l, u, settings=st)
+    ref = orc.solve_dense_qp_batch(P, qv, A, l, u, eps_abs=1e-8, eps_rel=1e-8)
+    assert np.all(res["status"] == 1) and np.all(ref["status"] == 1)
+    assert parity.rel_err(res["x"], ref["x"]).max() < 1e-5
+    assert parity.rel_err(res["y"], ref["y"]).max() < 1e-4
+
+
+def test_dense_qp_box_rows_equal_identity_rows():
+    """Box rows handled as a diagonal give the same answer as explicit identity rows of A."""
+    rng = np.random.default_rng(0)
+    P, qv, A, l, u = scenarios.synthetic_qps(4, 20, 10, seed=7)
+    lb, ub = -0.3 * np.ones((4, 8)), 0.2 * np.ones((4, 8))
+    Eb = np.zeros((4, 8, 20))
+    Eb[:, np.arange(8), 12 + np.arange(8)] = 1
+    st = OSQPSettings(eps_abs=1e-9, eps_rel=1e-9, max_iter=20000)
+    a = emu.solve_qp_batch(P, qv, A, l, u, lb, ub, settings=st)
+    b = emu.solve_qp_batch(P, qv, np.concatenate([A, Eb], 1), np.concatenate([l, lb], 1), np.concatenate([u, ub], 1),
+                           settings=st)
+    assert np.all(a["status"] == 1) and np.all(b["status"] == 1)
+    assert np.array_equal(a["iters"], b["iters"])
+    np.testing.assert_allclose(a["x"], b["x"], atol=1e-9)
+
+
+def test_infeasible_qp_is_reported(orc):
+    n = 4
+    P = np.eye(n)[None]
+    qv = np.ones((1, n))
+    A = np.array([[[1.0, 0, 0, 0], [1.0, 0, 0, 0]]])
+    l = np.array([[1.0, -5.0]])
+    u = np.array([[2.0, -4.0]])  # x0 in [1,2] and x0 in [-5,-4]
+    st = OSQPSettings(eps_abs=1e-6, eps_rel=1e-6, max_iter=4000)
+    res = emu.solve_qp_batch(P, qv, A, l, u, settings=st)
+    ref = orc.solve_dense_qp_batch(P, qv, A, l, u, eps_abs=1e-6, eps_rel=1e-6, max_iter=4000)
+    assert res["status"][0] == -3 and ref["status"][0] == -3

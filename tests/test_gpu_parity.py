@@ -1,0 +1,169 @@
+"""GPU parity tests proper: the CUDA path through the C ABI (libqpcontrol_b200.so) against the CPU oracle on the same
+seeded inputs.  Tolerances: joint torques / accelerations / contact wrenches within 1e-5 relative (fp64, north_star),
+identical accept/reject status and solution active contact sets."""
+import numpy as np
+import pytest
+
+import parity
+from qpcontrol_jl_b200 import (JointAccelerationTask, MomentumBasedController, OSQPSettings, SpatialAccelerationTask,
+                               scenarios)
+from qpcontrol_jl_b200.mechanism import PRISMATIC, REVOLUTE, rand_floating_humanoid, rand_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def test_atlas_standing_tick_matches_oracle(orc):
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    q, v = scenarios.atlas_random_states(mech, qnom, 96, seed=3)
+    res = ctrl(q, v)
+    ref = orc.OracleController(low.program).solve_batch(q, v)
+    assert np.all(res.status == 1)
+    parity.assert_tick_parity(res, ref, low.program)
+    assert np.all(res.tau[:, :6] == 0.0)
+    assert low.finalize().launch_count() >= 3
+
+
+def test_atlas_notebook_settings_reach_reference_tolerances(orc):
+    """At the notebook's eps = 1e-5 every solve reports residuals under OSQP's criteria and torques agree with the
+    tightly converged oracle to the accuracy that tolerance allows."""
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
+    q, v = scenarios.atlas_random_states(mech, qnom, 256, seed=3)
+    res = ctrl(q, v)
+    assert np.all(res.status == 1)
+    assert np.all(res.iters <= 5000)
+    low.program.settings = OSQPSettings.test_suite()
+    ref = orc.OracleController(low.program).solve_batch(q, v)
+    assert parity.rel_err(res.tau, ref["tau"]).max() < 5e-3
+
+
+def test_assembled_qp_matches_emulation():
+    """Stage-level: kinematics + assembly kernel output equals the single-thread compilation of the same body."""
+    from emu import emu
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    q, v = scenarios.atlas_random_states(mech, qnom, 8, seed=5)
+    a = low.finalize().assemble_host(q, v)
+    b = emu.EmuController(low.program).assemble(q, v)
+    for k in ("P", "q", "G", "lg", "ug", "lb", "ub", "desired"):
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-12, atol=1e-9, err_msg=k)
+
+
+def test_contact_masks_and_statuses(orc):
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    B = 64
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=4)
+    cm = scenarios.contact_masks(B, 8, seed=4)
+    cw = np.full((B, 8), 1e-3)
+    res = ctrl(q, v, cw, cm, check=False)
+    ref = orc.OracleController(low.program).solve_batch(q, v, cweight=cw, cmaxnf=cm)
+    parity.assert_tick_parity(res, ref, low.program)
+    ok = (res.status == 1) | (res.status == 2)
+    assert np.abs(res.wrenches[ok][(cm == 0)[ok]]).max(initial=0) < 1e-6
+
+
+def test_split_invariance():
+    """8(e): results do not depend on how the batch is split (what sharding across GPUs does)."""
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
+    q, v = scenarios.atlas_random_states(mech, qnom, 64, seed=6)
+    whole = ctrl(q, v)
+    parts = [ctrl(q[i:i + 16], v[i:i + 16]) for i in range(0, 64, 16)]
+    assert np.array_equal(whole.tau, np.concatenate([p.tau for p in parts]))
+    assert np.array_equal(whole.iters, np.concatenate([p.iters for p in parts]))
+
+
+@pytest.mark.parametrize("constrained", [True, False])
+def test_fixed_base_joint_space(orc, constrained):
+    rng = np.random.default_rng(42)
+    mech = rand_tree(rng, [PRISMATIC, REVOLUTE, REVOLUTE])
+    ctrl = MomentumBasedController(mech, OSQPSettings.test_suite())
+    for j in range(mech.nb):
+        t = JointAccelerationTask(mech, j)
+        ctrl.addtask(t) if constrained else ctrl.addtask(t, 1.0)
+        t.setdesired(rng.random(1))
+    q = np.stack([mech.rand_configuration(rng) for _ in range(5)])
+    v = rng.standard_normal((5, mech.nv))
+    res = ctrl(q, v)
+    ref = orc.OracleController(ctrl.program).solve_batch(q, v)
+    parity.assert_tick_parity(res, ref, ctrl.program)
+
+
+def test_spatial_acceleration_constraint_mode(orc):
+    rng = np.random.default_rng(533)
+    mech = rand_floating_humanoid(rng)
+    ctrl = MomentumBasedController(mech, OSQPSettings.test_suite(), floatingjoint=0)
+    body, base = mech.findbody("l_foot"), mech.findbody("r_hand")
+    task = SpatialAccelerationTask(mech, base, body, frame=base)
+    ctrl.addtask(task)
+    for j in range(mech.nb):
+        ctrl.regularize(j, 1.0)
+    task.setdesired(rng.random(6))
+    q = np.stack([mech.rand_configuration(rng) for _ in range(4)])
+    v = rng.standard_normal((4, mech.nv))
+    res = ctrl(q, v)
+    ref = orc.OracleController(ctrl.program).solve_batch(q, v)
+    parity.assert_tick_parity(res, ref, ctrl.program)
+
+
+def test_acrobot_point_task(orc):
+    mech, low, task = scenarios.acrobot_point_task()
+    q, v, des = scenarios.acrobot_random_inputs(mech, 4096, seed=2)
+    res = low(q, v, des)
+    ref = orc.OracleController(low.program).solve_batch(q[:256], v[:256], desired=des[:256])
+    sub = type(res)(res.tau[:256], res.vdot[:256], res.wrenches[:256], res.status[:256], res.iters[:256],
+                    res.residuals[:256])
+    parity.assert_tick_parity(sub, ref, low.program)
+
+
+@pytest.mark.parametrize("n,m", [(30, 30), (68, 71), (100, 100)])
+def test_dense_qp_batch(orc, n, m):
+    from qpcontrol_jl_b200 import _lib
+    P, qv, A, l, u = scenarios.synthetic_qps(16, n, m, seed=5)
+    st = OSQPSettings(eps_abs=1e-8, eps_rel=1e-8, max_iter=20000)
+    res = _lib.solve_qp_batch_host(P, qv, A, l, u, settings=st)
+    ref = orc.solve_dense_qp_batch(P, qv, A, l, u, eps_abs=1e-8, eps_rel=1e-8)
+    assert np.all(res["status"] == 1) and np.all(ref["status"] == 1)
+    assert parity.rel_err(res["x"], ref["x"]).max() < 1e-5
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 3 size (16384): size-independent properties instead of an oracle diff -- floating torques are
+    exactly zero, every solve is accepted, Newton-Euler holds through the returned wrenches' vertical sum, and the
+    result is bit-identical when the batch is permuted."""
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
+    B = 16384
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=3)
+    res = ctrl(q, v)
+    assert np.all(res.status == 1)
+    assert np.all(res.tau[:, :6] == 0.0)
+    fz = res.wrenches[:, :, 5].sum(1)
+    assert np.all(fz > 0.5 * mech.total_mass * 9.81) and np.all(fz < 1.5 * mech.total_mass * 9.81)
+    perm = np.random.default_rng(0).permutation(B)
+    res2 = ctrl(q[perm], v[perm])
+    assert np.array_equal(res2.tau, res.tau[perm])
+
+
+def test_device_pointer_path_matches_host_path():
+    import torch
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
+    B = 512
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=9)
+    host = ctrl(q, v)
+    dev = low.finalize()
+    dq, dv = torch.from_numpy(q).cuda(), torch.from_numpy(v).cuda()
+    out = dict(tau=torch.empty(B, mech.nv, dtype=torch.float64, device="cuda"),
+               vdot=torch.empty(B, mech.nv, dtype=torch.float64, device="cuda"),
+               wrench=torch.empty(B, 8, 6, dtype=torch.float64, device="cuda"),
+               status=torch.empty(B, dtype=torch.int32, device="cuda"),
+               iters=torch.empty(B, dtype=torch.int32, device="cuda"),
+               residuals=torch.empty(B, 2, dtype=torch.float64, device="cuda"))
+    dev.reserve(B)
+    dev.solve_device(B, dq, dv, out, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["tau"].cpu().numpy(), host.tau)
+    assert np.array_equal(out["status"].cpu().numpy(), host.status)
+
+
+def test_no_gpu_fallback_is_an_error():
+    """The product path must fail loudly, never silently fall back to a CPU implementation."""
+    from qpcontrol_jl_b200 import _lib
+    with pytest.raises(RuntimeError):
+        _lib.load("/nonexistent/libqpcontrol_b200.so")
