@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- Atlas standing QP-control solves/sec on N B200 (BASELINE.json `metric`), one process per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this framework (CUDA, sm_100a)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                    # N ranks, instances sharded, no data-path collective
+    python bench.py --impl reference ...                          # the CPU restatement of the reference on host cores
+
+One "step" = one control tick (state -> kinematics/dynamics terms -> QP assembly -> ADMM solve -> inverse dynamics
+-> torques) for a batch of `--batch` randomised Atlas states PER GPU (BASELINE config 3: 16,384 on one B200; the
+OSQP settings are the Atlas notebook's, reference notebooks/Standing controller.ipynb:66-71).  Weak scaling: every
+rank owns its own contiguous block of instances (seed offset by rank); nothing is exchanged on the data path
+(torch.distributed is used only for the barrier and the max-over-ranks of the device time).
+
+`value`     solves/s with the inputs resident in HBM, timed with CUDA events on the launching stream (per step, L2
+            flushed between steps), max over ranks.
+`e2e`       the same metric through the reference-facing call with HOST buffers (qpc_solve_batch, QPC_HOST_PTRS):
+            pinned host q/v in, tau/vdot/wrenches/status/iters/residuals out, copies inside the timed region.
+`roofline`  dominant kernel (the ADMM solve): SURVEY.md 8(d) algorithmic FLOPs W(n,m,K,R) per solve x batch / its
+            CUDA-event duration, against the fp64 DFMA peak measured live on the same device.
+`cpu_baseline` / `--impl reference`: oracle/ (CPU fp64 restatement of RBD + Parametron + OSQP, lifted sparse form,
+            OpenMP over instances) on the box's host cores -- "port", because Julia / OSQP.jl cannot run here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "atlas_standing_qp_control_solves_per_sec"
+UNIT = "solves/s"
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def algorithmic_flops(n, m, K, R):
+    """W(n,m,K,R) = R [n(n+1) m + n^3/3] + K [4nm + 2n^2 + 12(n+m)] + ceil(K/25) [2nm + 2n^2]."""
+    return R * (n * (n + 1) * m + n ** 3 / 3.0) + K * (4 * n * m + 2 * n * n + 12 * (n + m)) + \
+        np.ceil(K / 25.0) * (2 * n * m + 2 * n * n)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="qpc_clocks_", suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            self.f.close()
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+        except Exception:
+            return out
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[4 + k].strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def build_workload(batch, rank, settings_name):
+    import qpc_loader
+    qpc = qpc_loader.load()
+    settings = getattr(qpc.OSQPSettings, settings_name)()
+    return qpc, settings
+
+
+def run_reference(args, rank, world):
+    """The reference arm: oracle/ on the host cores (all threads), on a bounded sample of the same workload."""
+    if rank != 0:
+        return 0
+    import qpc_loader
+    qpc = qpc_loader.load()
+    from oracle import oracle as orc
+    settings = qpc.OSQPSettings.standing_notebook()
+    mech, low, ctrl, qnom = qpc.scenarios.atlas_standing(settings)
+    sample = args.cpu_sample
+    q, v = qpc.scenarios.atlas_random_states(mech, qnom, sample, seed=3)
+    oc = orc.OracleController(low.program)
+    oc.set_settings(settings, warm_start=0)
+    cores = orc.max_threads()
+    for _ in range(args.warmup):
+        oc.reset()
+        oc.solve_batch(q, v)
+    secs = []
+    for _ in range(args.steps):
+        oc.reset()
+        r = oc.solve_batch(q, v)
+        secs.append(r["seconds"])
+    total = float(np.sum(secs))
+    value = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "atlas_standing_randomised_states (BASELINE config 3), OSQP eps 1e-5 cold start",
+                   "batch_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} instances per step (seed 3), lifted sparse-LDL OSQP restatement, "
+                                   f"OpenMP over instances; Julia/QPControl.jl cannot run on this box"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "iters_mean": float(r["iters"].mean()),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="instances per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="instances per step of the CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--masks", action="store_true", help="BASELINE config 4: per-instance active contact sets")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the "
+                         "CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import qpc_loader
+    qpc = qpc_loader.load()
+    from qpcontrol_jl_b200 import _lib
+
+    settings = qpc.OSQPSettings.standing_notebook()
+    mech, low, ctrl, qnom = qpc.scenarios.atlas_standing(settings, device=local)
+    B = args.batch
+    # each rank owns its own block of instances: seed offset = rank (rank 0 = BASELINE config 3's seed 3)
+    q, v = qpc.scenarios.atlas_random_states(mech, qnom, B, seed=3 + 1000 * rank)
+    cw = cm = None
+    if args.masks:
+        cm = qpc.scenarios.contact_masks(B, len(low.program.contacts), seed=4 + 1000 * rank)
+        cw = np.full_like(cm, 1e-3)
+    dev = low.finalize()
+    dims = dev.dims
+    nv, nc = dims["nv"], dims["ncontacts"]
+    dev.reserve(B)
+    dev.h.sync_defaults()
+
+    cuda = torch.device("cuda", local)
+    dq, dv = torch.from_numpy(q).to(cuda), torch.from_numpy(v).to(cuda)
+    dcw = None if cw is None else torch.from_numpy(cw).to(cuda)
+    dcm = None if cm is None else torch.from_numpy(cm).to(cuda)
+    out = dict(tau=torch.empty(B, nv, dtype=torch.float64, device=cuda),
+               vdot=torch.empty(B, nv, dtype=torch.float64, device=cuda),
+               wrench=torch.empty(B, nc, 6, dtype=torch.float64, device=cuda),
+               status=torch.empty(B, dtype=torch.int32, device=cuda),
+               iters=torch.empty(B, dtype=torch.int32, device=cuda),
+               residuals=torch.empty(B, 2, dtype=torch.float64, device=cuda),
+               factorizations=torch.empty(B, dtype=torch.int32, device=cuda))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=cuda)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        dev.solve_device(B, dq, dv, out, contact_weight=dcw, contact_maxnormalforce=dcm, stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") -----------------------------------------------------------------------
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_device()
+    torch.cuda.synchronize()
+    launches0 = dev.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()  # L2 flush between timed steps, outside the per-step events
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_total = float(np.sum(ms_steps))
+    launches = dev.launch_count() - launches0
+
+    # stage split + roofline of the dominant kernel (ADMM), CUDA events recorded by the library on the same stream
+    dev.set_profiling(True)
+    stage = np.zeros(3)
+    nprof = min(args.steps, 5)
+    for _ in range(nprof):
+        flush.zero_()
+        step_device()
+        stage += np.array(dev.stage_times())
+    stage /= nprof
+    dev.set_profiling(False)
+    clocks = sampler.stop()
+
+    status = out["status"].cpu().numpy()
+    iters = out["iters"].cpu().numpy().astype(np.float64)
+    nfac = out["factorizations"].cpu().numpy().astype(np.float64)
+    accepted = float(np.mean((status == 1) | (status == 2)))
+
+    # ---- end to end through the host-pointer C-ABI call ("e2e") ---------------------------------------------------------
+    hq = torch.from_numpy(q).pin_memory()
+    hv = torch.from_numpy(v).pin_memory()
+    hcw = None if cw is None else torch.from_numpy(cw).pin_memory()
+    hcm = None if cm is None else torch.from_numpy(cm).pin_memory()
+    hres = qpc.BatchResult(tau=torch.empty(B, nv, dtype=torch.float64).pin_memory().numpy(),
+                           vdot=torch.empty(B, nv, dtype=torch.float64).pin_memory().numpy(),
+                           wrenches=torch.empty(B, nc, 6, dtype=torch.float64).pin_memory().numpy(),
+                           status=torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+                           iters=torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+                           residuals=torch.empty(B, 2, dtype=torch.float64).pin_memory().numpy())
+    h2d = hq.numel() * 8 + hv.numel() * 8 + (0 if hcw is None else 2 * hcw.numel() * 8)
+    d2h = sum(a.nbytes for a in (hres.tau, hres.vdot, hres.wrenches, hres.status, hres.iters, hres.residuals))
+
+    def step_host():
+        dev.solve_host_into(hq.numpy(), hv.numpy(), hres, None if hcw is None else hcw.numpy(),
+                            None if hcm is None else hcm.numpy())
+
+    for _ in range(args.warmup):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()  # synchronous: returns after the D2H copies completed
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_ok = float(np.mean((hres.status == 1) | (hres.status == 2)))
+
+    # ---- max over ranks -----------------------------------------------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e_s, stage[1]], dtype=torch.float64, device=cuda)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max, e2e_s_max, admm_ms = [float(x) for x in t.cpu()]
+    total_solves = B * world * args.steps
+    value = total_solves / (ms_total_max * 1e-3)
+    e2e_value = total_solves / e2e_s_max
+
+    if rank == 0:
+        K, R = float(iters.mean()), float(nfac.mean())
+        peak_tf = _lib.measure_fp64_peak(local)
+        n_c, m_c = 68, 71  # SURVEY.md 8(d) canonical condensed dims
+        n_x, m_x = dims["n"], dims["mg"] + dims["nbox"]
+        w_canon = float(algorithmic_flops(n_c, m_c, K, R))
+        w_exec = float(algorithmic_flops(n_x, m_x, K, R))
+        ach = w_canon * B / (admm_ms * 1e-3) / 1e12
+        ach_exec = w_exec * B / (admm_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        bytes_per_solve = 1632.0  # q,v,maxnormalforce in; tau,vdot,wrenches,status,iters,res out
+        hbm_ach = bytes_per_solve * B / (float(np.mean(ms_steps)) * 1e-3) / 1e9
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "admm_traffic.json")
+        if os.path.exists(tf):
+            try:
+                traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": ("atlas_standing_varying_contact_sets (BASELINE config 4)" if args.masks else
+                                    "atlas_standing_randomised_states (BASELINE config 3)"),
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"instance-shard x{world}, "
+                       "no collective", "osqp": "eps_abs=eps_rel=1e-5 max_iter=5000 adaptive_rho_interval=25 cold start",
+                       "qp_dims_solved": {"n": n_x, "m": m_x}, "l2": "flushed between steps (256 MiB memset)",
+                       "model": "atlas-topology 36-DoF humanoid, synthetic inertias (qpcontrol_jl_b200.mechanism.atlas_like)"},
+            "per_batch_latency_us": 1e3 * ms_total_max / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s_max / args.steps, "accepted_frac": e2e_ok},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "kernel": "qpc_admm_kernel", "achieved": ach, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": traffic,
+                         "peak_source": "measured live: dependent-chain-free DFMA loop on this device "
+                                        "(MEASURED_PEAKS.json carries no fp64 figure)",
+                         "flops_per_solve": w_canon, "dims": {"n": n_c, "m": m_c},
+                         "achieved_executed_dims": ach_exec, "frac_executed_dims": ach_exec / peak_tf if peak_tf else None,
+                         "flops_per_solve_executed_dims": w_exec, "iters_mean": K, "factorizations_mean": R,
+                         "kernel_ms": admm_ms,
+                         "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                                 "bytes_per_solve": bytes_per_solve}},
+            "stage_ms": {"assemble": float(stage[0]), "admm": float(stage[1]), "inverse_dynamics": float(stage[2])},
+            "accepted_frac": accepted, "iters_max": float(iters.max()), "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline:
+            from oracle import oracle as orc
+            sample = min(args.cpu_sample, B)
+            oc = orc.OracleController(low.program)
+            oc.set_settings(settings, warm_start=0)
+            kw = {}
+            if cm is not None:
+                kw = dict(cweight=cw[:sample], cmaxnf=cm[:sample])
+            oc.solve_batch(q[:64], v[:64])
+            oc.reset()
+            r = oc.solve_batch(q[:sample], v[:sample], **kw)
+            line["cpu_baseline"] = {"value": sample / r["seconds"], "unit": UNIT, "cores": orc.max_threads(),
+                                    "kind": "port", "sample": f"first {sample} instances of rank 0's batch, "
+                                    "oracle/ lifted sparse-LDL OSQP restatement, OpenMP over instances, cold start",
+                                    "iters_mean": float(r["iters"].mean())}
+            tau_dev = out["tau"][:sample].cpu().numpy()
+            ok = (r["status"] == 1) & (status[:sample] == 1)
+            err = np.abs(tau_dev[ok] - r["tau"][ok]).max(1) / np.maximum(1.0, np.abs(r["tau"][ok]).max(1))
+            line["cpu_baseline"]["tau_rel_diff_median"] = float(np.median(err)) if err.size else None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

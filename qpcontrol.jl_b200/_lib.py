@@ -261,6 +261,15 @@ class DeviceController:
                                                  None), "qpc_solve_batch")
         return res
 
+    def solve_host_into(self, q, v, res: BatchResult, contact_weight=None, contact_maxnormalforce=None):
+        """As `solve_host`, writing into caller-owned (e.g. pinned) buffers: no allocation, no marshalling copies."""
+        h = self.h
+        B = q.shape[0]
+        bi, bo = h.batch_in(q, v, None, contact_weight, contact_maxnormalforce), _batch_out(res)
+        check(self.lib, self.lib.qpc_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo), C.c_int32(HOST_PTRS),
+                                                 None), "qpc_solve_batch")
+        return res
+
     def solve_device(self, B: int, q, v, out: dict, desired=None, contact_weight=None, contact_maxnormalforce=None,
                      stream: int = 0):
         """Device pointers in/out (torch CUDA tensors or anything with `.data_ptr()`), asynchronous on `stream`
