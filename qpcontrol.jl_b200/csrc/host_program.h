@@ -167,8 +167,14 @@ inline std::string compile_program(const HostController& hc, DevProgram& p) {
   p.nvf = 0;
   for (int i = 0; i < m.nv; i++) p.vcol[i] = p.vfix_des[i] >= 0 ? -1 : p.nvf++;
   p.nbx = p.ncontacts * p.N;
-  p.n = p.nvf + p.nbx;
-  int row = 0, npath = 0, nw = 0;
+  // weighted tasks keep the reference's slack variables e == task_error with cost w e'e / e'We (momentum.jl:107-126):
+  // condensing them into J'WJ squares the Jacobian scale into P and makes OSQP's relative dual tolerance far looser
+  // than it is on the reference's own QP
+  p.ne = 0;
+  for (auto& t : hc.tasks)
+    if (t.mode != 0) p.ne += t.dim;
+  p.n = p.nvf + p.ne + p.nbx;
+  int row = 0, npath = 0, nw = 0, scol = p.nvf;
   for (int ti = 0; ti < p.ntasks; ti++) {
     const HostTask& t = hc.tasks[ti];
     DevTask& d = p.tasks[ti];
@@ -184,9 +190,14 @@ inline std::string compile_program(const HostController& hc, DevProgram& p) {
     for (int i = 0; i < 3; i++) d.point[i] = t.point[i];
     d.eliminated = (t.kind == 4 && t.mode == 0) ? 1 : 0;
     d.row0 = -1;
-    if (t.mode == 0 && !d.eliminated) {
+    d.scol0 = -1;
+    if (!d.eliminated) {
       d.row0 = row;
       row += t.dim;
+    }
+    if (t.mode != 0) {
+      d.scol0 = scol;
+      scol += t.dim;
     }
     d.w_off = nw;
     if (t.mode == 2) {
@@ -228,7 +239,7 @@ inline std::string compile_program(const HostController& hc, DevProgram& p) {
     const HostContact& hcn = hc.contacts[c];
     DevContact& d = p.contacts[c];
     d.body = hcn.body;
-    d.col0 = p.nvf + c * p.N;
+    d.col0 = p.nvf + p.ne + c * p.N;
     rotation_between_z(hcn.normal, d.Rz);
     for (int i = 0; i < 3; i++) d.pos[i] = hcn.pos[i];
     for (int g = 0; g < p.N; g++) {  // forcebasis (contacts.jl:16-23): unit vectors on the cone

@@ -274,14 +274,18 @@ QPC_DEV void kin_task_rows(const DevProgram* __restrict__ pg, KinSmem& s, const 
   QPC_SYNC();
 }
 
-// ---- QP assembly (condensed form) ------------------------------------------------------------------
-// x = (free vd, rho);  P = 2 sum J'WJ + 2 reg (+ 2 w_c B'B on the rho blocks), q = 2 sum J'W r;
-// general rows: hard tasks J x = -r, wrench balance S'(A vd - sum G_c rho_c) = S'(Wg - Adot v); box 0 <= rho <= maxrho.
-// r = b - desired + J_fixed vd_fixed accounts for velocities fixed by hard JointAccelerationTasks.
+// ---- QP assembly -------------------------------------------------------------------------------------------------------
+// x = (free vd, task-error slacks e, rho).  Cost: regularisation 2 reg on vd (momentum.jl:128-131), the weighted
+// tasks' w e'e / e'We on their slacks (momentum.jl:107-117), 2 w_c B'B on each contact's rho block (contacts.jl:75-79
+// with f = B rho substituted).  General rows (all equalities): hard tasks J vd = -r; weighted tasks J vd - e = -r
+// (momentum.jl:124); wrench balance S'(A vd - sum G_c rho_c) = S'(Wg - Adot v) (momentum.jl:162-193).
+// Box rows 0 <= rho <= maxrho (contacts.jl:64-65).  r = b - desired + J_fixed vd_fixed accounts for velocities fixed
+// by hard JointAccelerationTasks, which are substituted out.  Contact force / wrench variables of the reference's
+// lifted QP (contacts.jl:46-48,63,66,67) are eliminated through their defining equalities.
 // P, qv, G, lg, ug, lb, ub point at this instance's slots (global or shared memory).
 QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double* P, double* qv, double* G, double* lg,
                           double* ug, double* lb, double* ub) {
-  const int n = pg->n, nv = pg->nv, mg = pg->mg, N = pg->N, nvf = pg->nvf;
+  const int n = pg->n, nv = pg->nv, mg = pg->mg, N = pg->N;
   const int t0 = QPC_TID, nt = QPC_NT;
   for (int i = t0; i < n * n; i += nt) P[i] = 0.0;
   for (int i = t0; i < mg * n; i += nt) G[i] = 0.0;
@@ -313,44 +317,21 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
       r[k] = a;
     }
     QPC_SYNC();
-    if (t.mode == 0) {
-      for (int k = t0; k < t.dim * nv; k += nt) {
-        const int row = k / nv, i = k % nv;
-        if (pg->vcol[i] >= 0) G[(t.row0 + row) * n + pg->vcol[i]] = s.Jt[k];
-      }
-      for (int k = t0; k < t.dim; k += nt) lg[t.row0 + k] = ug[t.row0 + k] = -r[k];
-    } else {
-      // P_vv += 2 J'WJ, q_v += 2 J'W r
-      const double* W = pg->Wbuf + t.w_off;
-      for (int k = t0; k < nv * nv; k += nt) {
-        const int i = k / nv, j = k % nv;
-        const int ci = pg->vcol[i], cj = pg->vcol[j];
-        if (ci < 0 || cj < 0) continue;
-        double a = 0;
-        if (t.mode == 1) {
-          for (int rr = 0; rr < t.dim; rr++) a += s.Jt[rr * nv + i] * s.Jt[rr * nv + j];
-          a *= t.weight;
-        } else {
-          for (int rr = 0; rr < t.dim; rr++)
-            for (int ss = 0; ss < t.dim; ss++)
-              a += 0.5 * s.Jt[rr * nv + i] * (W[rr * t.dim + ss] + W[ss * t.dim + rr]) * s.Jt[ss * nv + j];
+    for (int k = t0; k < t.dim * nv; k += nt) {
+      const int row = k / nv, i = k % nv;
+      if (pg->vcol[i] >= 0) G[(t.row0 + row) * n + pg->vcol[i]] = s.Jt[k];
+    }
+    for (int k = t0; k < t.dim; k += nt) lg[t.row0 + k] = ug[t.row0 + k] = -r[k];
+    if (t.mode != 0) {
+      for (int k = t0; k < t.dim; k += nt) G[(t.row0 + k) * n + t.scol0 + k] = -1.0;
+      if (t.mode == 1) {
+        for (int k = t0; k < t.dim; k += nt) P[(t.scol0 + k) * n + t.scol0 + k] = 2.0 * t.weight;
+      } else {  // e'We with a possibly unsymmetric W: the Hessian is W + W'
+        const double* W = pg->Wbuf + t.w_off;
+        for (int k = t0; k < t.dim * t.dim; k += nt) {
+          const int a = k / t.dim, b = k % t.dim;
+          P[(t.scol0 + a) * n + t.scol0 + b] = W[a * t.dim + b] + W[b * t.dim + a];
         }
-        P[ci * n + cj] += 2.0 * a;
-      }
-      for (int i = t0; i < nv; i += nt) {
-        const int ci = pg->vcol[i];
-        if (ci < 0) continue;
-        double a = 0;
-        if (t.mode == 1) {
-          for (int rr = 0; rr < t.dim; rr++) a += s.Jt[rr * nv + i] * r[rr];
-          a *= t.weight;
-        } else {
-          // x'Wx with a possibly unsymmetric W: gradient uses (W + W')/2
-          for (int rr = 0; rr < t.dim; rr++)
-            for (int ss = 0; ss < t.dim; ss++)
-              a += 0.5 * s.Jt[rr * nv + i] * (W[rr * t.dim + ss] + W[ss * t.dim + rr]) * r[ss];
-        }
-        qv[ci] += 2.0 * a;
       }
     }
     QPC_SYNC();
@@ -371,7 +352,7 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
     }
     for (int k = t0; k < 6 * pg->ncontacts * N; k += nt) {
       const int kk = k / (pg->ncontacts * N), cg = k % (pg->ncontacts * N);
-      G[(row0 + kk) * n + nvf + cg] = -dot(ld6(s.SW + 6 * (o + kk)), ld6(s.GC + 6 * cg));
+      G[(row0 + kk) * n + pg->contacts[cg / N].col0 + cg % N] = -dot(ld6(s.SW + 6 * (o + kk)), ld6(s.GC + 6 * cg));
     }
     for (int kk = t0; kk < 6; kk += nt) {
       double a = dot(ld6(s.SW + 6 * (o + kk)), ld6(s.tot + 15) - ld6(s.tot + 9));
@@ -381,14 +362,13 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
     }
     QPC_SYNC();
   }
-  // symmetrise P against summation-order noise: not needed, the accumulation above is symmetric by construction
 }
 
 // ---- epilogue: contact wrenches, inverse dynamics (momentum.jl:62-80) ------------------------------------------------
 // x = condensed solution.  Writes vd (nv), per-contact world wrenches (nc x 6) and tau (nv) to the given slots.
 QPC_DEV void kin_inverse_dynamics(const DevProgram* __restrict__ pg, KinSmem& s, const double* x, double* vd_out,
                                   double* wrench_out, double* tau_out) {
-  const int nv = pg->nv, nb = pg->nb, N = pg->N, nvf = pg->nvf;
+  const int nv = pg->nv, nb = pg->nb, N = pg->N;
   double* vd = s.Jt;            // nv
   double* ext = s.scr;          // nb * 6 external wrench per body (then joint wrenches)
   double* acc = s.scr + 6 * nb; // nb * 6 spatial accelerations
@@ -403,7 +383,7 @@ QPC_DEV void kin_inverse_dynamics(const DevProgram* __restrict__ pg, KinSmem& s,
   for (int k = QPC_TID; k < pg->ncontacts * 6; k += QPC_NT) {
     const int c = k / 6, r = k % 6;
     double a = 0;
-    for (int g = 0; g < N; g++) a += x[nvf + c * N + g] * s.GC[6 * (c * N + g) + r];
+    for (int g = 0; g < N; g++) a += x[pg->contacts[c].col0 + g] * s.GC[6 * (c * N + g) + r];
     if (wrench_out) wrench_out[k] = a;
     s.A[k] = a;  // A is free now: stash per-contact wrenches
   }

@@ -24,7 +24,8 @@ struct Settings {
 
 struct DevTask {
   int kind, mode, dim, source, target, frame, joint, des_off;
-  int row0;                // first row in G (hard, not eliminated) or -1
+  int row0;                // first row in G (hard: task_error == 0; weighted: e == task_error) or -1 when eliminated
+  int scol0;               // first slack column in x (weighted tasks, momentum.jl:119-126) or -1
   int path_ptr, path_len;  // entries of path_body / path_sign
   int w_off;               // matrix weight offset in Wbuf
   int eliminated;          // hard joint task: its velocities are substituted, no rows
@@ -53,7 +54,8 @@ struct DevProgram {
   // ---- program ---------------------------------------------------------------------------------------------
   int N, floating;  // floating = successor body of the floating joint or -1
   int ntasks, ncontacts, ndes;
-  int n, nvf, mg, nbx;  // condensed QP: n = nvf + ncontacts*N variables, mg general rows, nbx box rows (the rhos)
+  int n, nvf, ne, mg, nbx;  // QP the device solves: x = (free vd [nvf], task-error slacks e [ne], rho [nbx]);
+                            // mg general (equality) rows, nbx box rows 0 <= rho <= maxrho
   int balance_row0;
   int vcol[QPC_MAXV];      // column of velocity i in x, or -1 when fixed by a hard JointAccelerationTask
   int vfix_des[QPC_MAXV];  // desired offset providing the value of a fixed velocity

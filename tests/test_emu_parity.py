@@ -20,7 +20,7 @@ def test_atlas_standing_tick(orc):
     assert np.all(res.tau[:, :6] == 0.0)
     assert (low.finalize if False else True)
     h = emu.EmuController(low.program).h
-    assert (h.n, h.mg, h.nbox) == (50, 21, 32)  # 18 free vd + 32 rho; feet 12 + pelvis 3 + balance 6
+    assert (h.n, h.mg, h.nbox) == (53, 24, 32)  # 18 free vd + 3 slack + 32 rho; feet 12 + linmom 3 + pelvis 3 + balance 6
 
 
 def test_atlas_contact_masks(orc):
@@ -39,7 +39,7 @@ def test_atlas_contact_masks(orc):
 
 
 def test_condensed_qp_matches_lifted_solution(orc):
-    """The oracle's lifted solution satisfies the condensed constraints and is stationary for the condensed cost."""
+    """The oracle's lifted solution satisfies the device QP's constraints and is stationary for its cost."""
     mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
     q, v = scenarios.atlas_random_states(mech, qnom, 3, seed=8)
     oc = orc.OracleController(low.program)
@@ -52,16 +52,17 @@ def test_condensed_qp_matches_lifted_solution(orc):
             fixed[list(mech.velocity_range(e.task.joint))] = True
     for i in range(3):
         xl = o["x_lifted"][i]
-        x = np.concatenate([o["vd"][i][~fixed]] + [xl[36 + 13 * c:36 + 13 * c + 4] for c in range(8)])
+        # device order: free vd, the weighted task's slack e (last 3 lifted variables), rho of every contact
+        x = np.concatenate([o["vd"][i][~fixed], xl[36 + 13 * 8:]] + [xl[36 + 13 * c:36 + 13 * c + 4] for c in range(8)])
         np.testing.assert_allclose(a["G"][i] @ x, a["lg"][i], atol=1e-6)
         assert np.array_equal(a["lg"][i], a["ug"][i])
-        assert np.all(x[18:] >= -1e-7) and np.all(x[18:] <= a["ub"][i] + 1e-7)
+        assert np.all(x[21:] >= -1e-7) and np.all(x[21:] <= a["ub"][i] + 1e-7)
         P = a["P"][i]
         np.testing.assert_allclose(P, P.T, atol=1e-12)
         # stationarity on the free (inactive-bound) coordinates, projected on the null space of G
         g = P @ x + a["q"][i]
-        act = x[18:] < 1e-7
-        free = np.concatenate([np.ones(18, bool), ~act])
+        act = x[21:] < 1e-7
+        free = np.concatenate([np.ones(21, bool), ~act])
         Gf = a["G"][i][:, free]
         y, *_ = np.linalg.lstsq(Gf.T, -g[free], rcond=None)
         assert np.abs(g[free] + Gf.T @ y).max() < 1e-5 * max(1.0, np.abs(g).max())
