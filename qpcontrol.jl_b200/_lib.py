@@ -16,7 +16,8 @@ from .controller import BatchResult
 from .program import OSQPSettings, Program
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libqpcontrol_b200.so")
+# QPC_LIB_PATH: developer override used to A/B two builds of the same CUDA library on the GPU box
+LIB_PATH = os.environ.get("QPC_LIB_PATH") or os.path.join(_HERE, "csrc", "libqpcontrol_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -1,0 +1,658 @@
+// admm_reg.cuh -- OSQP-style ADMM with the KKT inverse held in registers (sm_100a), one QP per CTA.
+//
+//   min 1/2 x'Px + q'x   s.t.  lg <= G x <= ug (mg general rows),  lb <= x[n-nbx..n) <= ub (nbx box rows)
+//
+// Device-side replacement for `MOI.optimize!(::OSQP.Optimizer)` reached by `solve!(qpmodel)` (reference
+// src/lowlevel/momentum.jl:58; solver plugged in at momentum.jl:1,15-16,27).  Same algorithm and constants as admm.cuh
+// (OSQP 0.5.x): Ruiz equilibration, per-row rho, relaxed ADMM, unscaled termination residuals every
+// `check_termination` iterations, infeasibility certificates, adaptive rho with refactorisation.  What differs is the
+// machine mapping:
+//
+//  * The quasi-definite KKT matrix  Z = [[-diag(1/rho), G], [G', P + sigma I + box terms]]  (NK = mg + n rows, padded
+//    with an identity block to NP = 8 TC positions) lives in REGISTERS as 4 x TC tiles: thread t holds rows
+//    4(t/8)..4(t/8)+3 and columns (t%8) TC .. (t%8) TC + TC-1.  Every vector element fetched from shared memory feeds
+//    4 DFMAs, which keeps the 128 B/clk shared-memory pipe below the fp64 pipe (a 1 x C row layout is bound by it).
+//    Box rows are a diagonal and are folded into the x-row that owns the variable.
+//  * "Factorisation" = NP symmetric sweep steps turning the registers into -Z^-1 in place: per step the pivot row is
+//    broadcast through shared memory and every thread does 4 TC DFMAs on its tile; one barrier per step.  The tile
+//    columns rotate by one register per step so the pivot column is always register 0 and the new inverse column is
+//    inserted at register TC-1 (no dynamic register index); after NP steps the rotation is the identity again.
+//  * An ADMM iteration is ONE matrix-vector product  [nu; x~] = Z^-1 [z - y/rho; sigma x - q + box]  : 4 TC DFMAs per
+//    thread against a double-buffered vector in shared memory, a 4-shuffle transpose-reduction over the 8 lanes of a
+//    row group that leaves each lane with the entry of the row it owns, the projection / dual update in that lane's
+//    registers, one barrier per iteration.
+//  * Ruiz equilibration works on the same tiles: by symmetry of the KKT matrix the column norms are the row norms.
+//  * The scaled, unswept matrix is kept in shared memory (thread-major, conflict-free) for the residual products of
+//    the termination / adaptive-rho checks and for refactorisation after a rho update.
+#pragma once
+#include "admm.cuh"
+
+namespace qpc {
+
+constexpr int REG_MAXW = 12;  // warps per CTA supported by the reduction scratch
+constexpr int REG_NB = 8;     // column blocks (lanes per row group)
+constexpr int REG_TR = 4;     // rows per thread
+
+QPC_HD int admm_reg_positions(int TC) { return REG_NB * TC; }
+QPC_HD int admm_reg_threads(int TC) { return 2 * REG_NB * TC; }  // (NP / 4 row groups) x 8 column blocks
+QPC_HD int admm_reg_smem_doubles(int TC) {
+  const int NP = REG_NB * TC;
+  return REG_TR * TC * admm_reg_threads(TC) + 2 * (NP + 2) + 2 * NP + 3 * REG_MAXW * 16 + 13 * NP + 16;
+}
+
+#if defined(__CUDACC__)
+
+// warp-wide maximum of NON-NEGATIVE doubles (NaN sorts above +inf and is therefore propagated): their IEEE bit
+// patterns order like unsigned integers, so two 32-bit redux.sync operations do it
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double warp_sum(double a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
+// block reduction of KM maxima of non-negative values followed by KS sums; every thread gets the (bitwise identical)
+// result.  `red2` alternates between two buffers so no trailing barrier is needed.
+template <int KM, int KS>
+__device__ __forceinline__ void reg_block_reduce(double (&v)[KM + KS], double* red2, int& sel) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* red = red2 + sel * (REG_MAXW * 16);
+  sel ^= 1;
+#pragma unroll
+  for (int k = 0; k < KM + KS; k++) {
+    const double a = k < KM ? warp_max_nonneg(v[k]) : warp_sum(v[k]);
+    if (lane == 0) red[warp * 16 + k] = a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < KM + KS; k++) {
+    const double t = lane < nw ? red[lane * 16 + k] : 0.0;
+    v[k] = k < KM ? warp_max_nonneg(t) : warp_sum(t);
+  }
+}
+
+// The same reduction split in two so that the 15 residual quantities never have to be live at once: stage 1 reduces
+// one value over the warp and parks it, stage 2 (after a barrier) combines the warps' entries on demand.
+template <bool IS_MAX>
+__device__ __forceinline__ void red_put(double* red, int k, double v) {
+  const double a = IS_MAX ? warp_max_nonneg(v) : warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[(threadIdx.x >> 5) * 16 + k] = a;
+}
+template <bool IS_MAX>
+__device__ __forceinline__ double red_get(const double* red, int k) {
+  const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const double t = lane < nw ? red[lane * 16 + k] : 0.0;
+  return IS_MAX ? warp_max_nonneg(t) : warp_sum(t);
+}
+
+// Transpose-reduction over the 8 lanes (column blocks) of a row group: every lane enters with partial results for
+// its 4 tile rows and leaves with the complete result of row (q >> 1) & 3, the row it owns.  4 exchanges.
+template <bool IS_MAX>
+__device__ __forceinline__ double group_reduce(const double (&s)[REG_TR], int q) {
+  auto comb = [](double a, double b) { return IS_MAX ? fmax(a, b) : a + b; };
+  const bool hi4 = q & 4, hi2 = q & 2;
+  const double k0 = hi4 ? s[2] : s[0], k1 = hi4 ? s[3] : s[1];
+  const double o0 = hi4 ? s[0] : s[2], o1 = hi4 ? s[1] : s[3];
+  const double r0 = comb(k0, __shfl_xor_sync(0xffffffffu, o0, 4));
+  const double r1 = comb(k1, __shfl_xor_sync(0xffffffffu, o1, 4));
+  const double k = hi2 ? r1 : r0, o = hi2 ? r0 : r1;
+  double v = comb(k, __shfl_xor_sync(0xffffffffu, o, 2));
+  v = comb(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return v;
+}
+
+template <int TC>
+struct RegSolver {
+  static constexpr int NP = REG_NB * TC;      // row / column positions: general rows (mg), x rows (n), padding
+  static constexpr int NT = 2 * REG_NB * TC;  // threads
+  static constexpr int TR = REG_TR;
+  static constexpr int US = NP + 2;           // stride of the double-buffered vectors
+  // ---- geometry -------------------------------------------------------------------------------------------------
+  int n, mg, nbx, NK, tid, q, g, row, h, c0;  // q: column block, g: row group, row: the row this lane owns
+  bool isx, isg, hasbox, hasc;  // x-row / general-constraint row / x-row that also owns a box row / owns any row
+  // ---- shared memory -----------------------------------------------------------------------------------------------
+  double *K0, *uv, *cv, *red, *SC;
+  // SC: per-position constants, 13 arrays of NP: 0 q | 1 l | 2 u | 3 cb | 4 rho | 5 1/rho | 6 D | 7 E(box) | 8 diag |
+  //     9 xprev | 10 yprev | 11 scalars | 12 cb rho
+  int redsel;
+  // ---- registers: the tile and the state of the owned row -----------------------------------------------------------
+  double a[TR][TC];
+  double x, z, y;
+
+  __device__ __forceinline__ double& sc(int k, int pos) const { return SC[k * NP + pos]; }
+
+  __device__ __forceinline__ double rho_of(double rho0) const {
+    const double l = sc(1, row), u = sc(2, row);
+    if (l < -QPC_INFTY * QPC_MIN_SCALING && u > QPC_INFTY * QPC_MIN_SCALING) return QPC_RHO_MIN;
+    if (u - l < QPC_RHO_TOL) return QPC_RHO_EQ_FACTOR * rho0;
+    return rho0;
+  }
+
+  __device__ __forceinline__ void load_tile() {
+#pragma unroll
+    for (int r = 0; r < TR; r++)
+#pragma unroll
+      for (int c = 0; c < TC; c++) a[r][c] = K0[(r * TC + c) * NT + tid];
+  }
+  __device__ __forceinline__ void store_tile() {
+#pragma unroll
+    for (int r = 0; r < TR; r++)
+#pragma unroll
+      for (int c = 0; c < TC; c++) K0[(r * TC + c) * NT + tid] = a[r][c];
+  }
+
+  // a <- -(Z^-1) by NP symmetric sweep steps, pivot position s at step s (the -1/rho block first, then the by then
+  // positive definite x block, then the identity padding).  See the header for the rotation.
+  __device__ __forceinline__ void factor(double sigma) {
+    if (h == 0) {
+      const double cb = sc(3, row), rho = sc(4, row), rinv = sc(5, row);
+      sc(8, row) = isx ? sigma + (hasbox ? rho * cb * cb : 0.0) : (isg ? -rinv : 1.0);
+    }
+    load_tile();
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < TR; r++) {
+      const int pos = 4 * g + r, ck = pos - c0;
+      const double dd = sc(8, pos);
+#pragma unroll
+      for (int c = 0; c < TC; c++)
+        if (c == ck) a[r][c] += dd;
+    }
+    double* pb = uv;  // 2 x (NP + 2): published pivot row (raw register dump of the 8 column blocks), then 1/pivot
+    if (g == 0) {
+      double2* pw = reinterpret_cast<double2*>(pb + c0);
+#pragma unroll
+      for (int c = 0; c < TC / 2; c++) pw[c] = make_double2(a[0][2 * c], a[0][2 * c + 1]);
+      if (q == 0) pb[NP] = 1.0 / a[0][0];
+    }
+    __syncthreads();
+    for (int s4 = 0; s4 < NP / 4; s4++) {
+#pragma unroll
+      for (int rr = 0; rr < TR; rr++) {
+        const int s = 4 * s4 + rr;
+        const double* pr = pb + (s & 1) * US;
+        const int b = s / TC, sm = s - b * TC;  // pivot column block and rotation count (mod TC)
+        const double dinv = pr[NP];
+        const double2* p2 = reinterpret_cast<const double2*>(pr + c0);
+        double f[TR];
+#pragma unroll
+        for (int r = 0; r < TR; r++) {
+          const int pos = 4 * g + r, blk = pos / TC;
+          int ci = pos - blk * TC - sm;
+          ci += ci < 0 ? TC : 0;
+          f[r] = pr[blk * TC + ci] * dinv;
+        }
+        const bool inb = q == b;
+        const bool own = g == s4;
+        double t0[TR];
+#pragma unroll
+        for (int r = 0; r < TR; r++) t0[r] = a[r][0];
+        const double p0 = pr[c0];
+        // a[r][c-1] <- a[r][c] - f[r] p[c]  (the pivot row itself: a[r][c] / pivot), two columns per 16-byte load
+#pragma unroll
+        for (int c2 = 0; c2 < TC / 2; c2++) {
+          const double2 v = p2[c2];
+#pragma unroll
+          for (int r = 0; r < TR; r++) {
+            if (r == rr && own) {
+              if (c2 > 0) a[r][2 * c2 - 1] = a[r][2 * c2] * dinv;
+              a[r][2 * c2] = a[r][2 * c2 + 1] * dinv;
+            } else {
+              if (c2 > 0) a[r][2 * c2 - 1] = fma(-f[r], v.x, a[r][2 * c2]);
+              a[r][2 * c2] = fma(-f[r], v.y, a[r][2 * c2 + 1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < TR; r++) {
+          if (r == rr && own) a[r][TC - 1] = inb ? -dinv : t0[r] * dinv;
+          else a[r][TC - 1] = inb ? f[r] : fma(-f[r], p0, t0[r]);
+        }
+        // publish the next pivot row (position s + 1: row group (s + 1) / 4, tile row (rr + 1) % 4)
+        const int s1 = s + 1;
+        constexpr int TRm = TR - 1;
+        const int rn = (rr + 1) & TRm;
+        if (s1 < NP && g == (s1 >> 2)) {
+          double* pw = pb + (s1 & 1) * US;
+          double2* pw2 = reinterpret_cast<double2*>(pw + c0);
+#pragma unroll
+          for (int c = 0; c < TC / 2; c++) pw2[c] = make_double2(a[rn][2 * c], a[rn][2 * c + 1]);
+          if (q == s1 / TC) pw[NP] = 1.0 / a[rn][0];
+        }
+        __syncthreads();
+      }
+    }
+  }
+
+  // right-hand side entry of the owned row for the next KKT solve; w = z - y / rho
+  __device__ __forceinline__ double rhs_entry(double sigma) const {
+    const double w = hasc ? fma(-y, sc(5, row), z) : 0.0;
+    if (isg) return w;
+    if (isx) return fma(sigma, x, -sc(0, row)) + (hasbox ? sc(12, row) * w : 0.0);
+    return 0.0;
+  }
+  __device__ __forceinline__ void set_rho(double rho0) {  // owner lanes: per-row rho and what depends on it
+    const double r = rho_of(rho0);
+    sc(4, row) = r;
+    sc(5, row) = 1.0 / r;
+    sc(12, row) = sc(3, row) * r;
+  }
+
+  // one ADMM iteration of the owned row given the KKT solve result t, written so that the
+  // dependent chain after t is as short as possible
+  __device__ __forceinline__ void update_row(double t, double alpha, double oma) {
+    if (isx) x = fma(alpha, t, oma * x);
+    if (hasc) {
+      const double rinv = sc(5, row), rho = sc(4, row), lo = sc(1, row), up = sc(2, row);
+      const double zt = isg ? fma(t, rinv, fma(-y, rinv, z)) : sc(3, row) * t;  // z - y/rho does not wait for t
+      const double zr = fma(alpha, zt, oma * z);
+      double zn = fma(y, rinv, zr);
+      zn = zn < lo ? lo : zn;
+      zn = zn > up ? up : zn;
+      y = fma(rho, zr - zn, y);
+      z = zn;
+    }
+  }
+
+  // tile times a vector in shared memory -> the entry of the owned row
+  __device__ __forceinline__ double tile_dot(const double* __restrict__ vec) const {
+    const double2* v2 = reinterpret_cast<const double2*>(vec + c0);
+    double s0[TR];
+#pragma unroll
+    for (int r = 0; r < TR; r++) s0[r] = 0.0;
+#pragma unroll
+    for (int c = 0; c < TC / 2; c++) {
+      const double2 v = v2[c];
+#pragma unroll
+      for (int r = 0; r < TR; r++) s0[r] = fma(a[r][2 * c + 1], v.y, fma(a[r][2 * c], v.x, s0[r]));
+    }
+    return group_reduce<false>(s0, q);
+  }
+
+  // products of the owned row of the scaled, unswept matrix: x-rows get (P vx, G' vy), general rows get (G vx, 0)
+  __device__ __forceinline__ void k0_products(const double* vx, const double* vy, double& px, double& py) const {
+    double s0[TR], s1[TR];
+#pragma unroll
+    for (int r = 0; r < TR; r++) s0[r] = s1[r] = 0.0;
+#pragma unroll
+    for (int c = 0; c < TC; c++) {
+      const double ex = vx[c0 + c], ey = vy[c0 + c];
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        const double m = K0[(r * TC + c) * NT + tid];
+        s0[r] = fma(m, ex, s0[r]);
+        s1[r] = fma(m, ey, s1[r]);
+      }
+    }
+    px = group_reduce<false>(s0, q);
+    py = group_reduce<false>(s1, q);
+  }
+
+  __device__ void solve(const Settings& st, const AdmmProblem& pb_, double* smem) {
+    tid = threadIdx.x;
+    q = tid & 7;
+    g = tid >> 3;
+    c0 = q * TC;
+    row = 4 * g + ((q >> 1) & 3);
+    h = q & 1;
+    NK = n + mg;
+    isg = row < mg;
+    isx = row >= mg && row < NK;
+    const int xi = row - mg;
+    hasbox = isx && xi >= n - nbx;
+    hasc = hasbox || isg;
+    K0 = smem;
+    uv = K0 + TR * TC * NT;        // 2 x (NP + 2)
+    cv = uv + 2 * US;              // 2 x NP
+    red = cv + 2 * NP;             // 3 x REG_MAXW x 16 (two alternating buffers + the residual check's own)
+    SC = red + 3 * REG_MAXW * 16;  // 13 x NP
+    redsel = 0;
+    const int m = mg + nbx;
+    // ---- load: coalesced global reads, scattered into the thread-major staging area ----------------------------------
+    for (int k = tid; k < TR * TC * NT; k += NT) K0[k] = 0.0;
+    for (int k = tid; k < 2 * US + 2 * NP; k += NT) uv[k] = 0.0;
+    __syncthreads();
+    auto k0_index = [&](int i, int j) {  // element (row position i, column position j)
+      const int qq = j / TC;
+      return ((i & 3) * TC + (j - qq * TC)) * NT + (i >> 2) * 8 + qq;
+    };
+    for (int k = tid; k < n * n; k += NT) {
+      const int i = k / n, j = k - i * n;
+      K0[k0_index(mg + i, mg + j)] = pb_.P[k];
+    }
+    for (int k = tid; k < mg * n; k += NT) {
+      const int r = k / n, j = k - r * n;
+      const double gv = pb_.G[k];
+      K0[k0_index(r, mg + j)] = gv;
+      K0[k0_index(mg + j, r)] = gv;
+    }
+    x = 0.0;
+    z = 0.0;
+    y = 0.0;
+    double qs = 0.0, cb = 0.0, l = 0.0, u = 0.0;
+    double D = 1.0, E = 1.0;  // accumulated Ruiz scalings of the owned row (E: its constraint row)
+    if (isx) qs = pb_.qv[xi];
+    if (isg) {
+      l = fmax(pb_.lg[row], -QPC_INFTY);
+      u = fmin(pb_.ug[row], QPC_INFTY);
+    } else if (hasbox) {
+      const int b = xi - (n - nbx);
+      l = fmax(pb_.lb[b], -QPC_INFTY);
+      u = fmin(pb_.ub[b], QPC_INFTY);
+      cb = 1.0;
+    }
+    __syncthreads();
+    load_tile();
+    // ---- Ruiz equilibration of [P A'; A 0]; A = [G; E_box] -----------------------------------------
+    double cscale = 1.0;
+    double* sv = cv;  // scale vector broadcast, NP entries
+    for (int it = 0; it < st.scaling; it++) {
+      double nr4[TR];
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < TC; c++) v = fmax(v, fabs(a[r][c]));
+        nr4[r] = v;
+      }
+      double nr = group_reduce<true>(nr4, q);
+      if (hasbox) nr = fmax(nr, fabs(cb));
+      const double sr = row < NK ? 1.0 / sqrt(limit_scaling(nr)) : 1.0;
+      const double eb = hasbox ? 1.0 / sqrt(limit_scaling(fabs(cb))) : 1.0;
+      if (h == 0) sv[row] = sr;
+      __syncthreads();
+      {
+        double sc4[TR];
+#pragma unroll
+        for (int r = 0; r < TR; r++) sc4[r] = sv[4 * g + r];
+#pragma unroll
+        for (int c = 0; c < TC; c++) {
+          const double scol = sv[c0 + c];
+#pragma unroll
+          for (int r = 0; r < TR; r++) a[r][c] *= sc4[r] * scol;
+        }
+      }
+      if (isx) {
+        qs *= sr;
+        D *= sr;
+        if (hasbox) {
+          cb *= eb * sr;
+          E *= eb;
+        }
+      } else if (isg) {
+        E *= sr;
+      }
+      // cost scaling: mean column norm of P_bar (= row norms of the x block, by symmetry) vs |q_bar|_inf
+      double pn4[TR];
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        double v = 0.0;
+        const bool xr = 4 * g + r >= mg;
+#pragma unroll
+        for (int c = 0; c < TC; c++)
+          if (xr && c0 + c >= mg) v = fmax(v, fabs(a[r][c]));
+        pn4[r] = v;
+      }
+      const double pn = group_reduce<true>(pn4, q);
+      double v2[2];
+      v2[0] = isx ? fabs(qs) : 0.0;
+      v2[1] = (isx && h == 0) ? pn : 0.0;
+      reg_block_reduce<1, 1>(v2, red, redsel);
+      double ct = limit_scaling(n > 0 ? v2[1] / n : 1.0);
+      const double qn = limit_scaling(v2[0]);
+      ct = 1.0 / fmax(ct, qn);
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        const bool xr = 4 * g + r >= mg;
+#pragma unroll
+        for (int c = 0; c < TC; c++)
+          if (xr && c0 + c >= mg) a[r][c] *= ct;
+      }
+      if (isx) qs *= ct;
+      cscale *= ct;
+    }
+    l *= E;
+    u *= E;
+    store_tile();
+    // Control block in shared memory (written by thread 0 at the end of every residual check, read by everyone after
+    // the barrier): keeping these scalars out of the register file leaves the plain-iteration loop with nothing live
+    // but the tile, the row state and a few pointers.
+    double* CD = &sc(11, 0);                    // 0 cscale | 1 1/cscale | 2 rho | 3 pri_res | 4 dua_res
+    int* CI = reinterpret_cast<int*>(CD + 8);   // 0 status | 1 iter | 2 nfac | 3 next check | 4 next adapt | 5 refactor | 6 done
+    const int chk_iv = st.check_termination, ada_iv = (st.adaptive_rho && st.adaptive_rho_interval) ? st.adaptive_rho_interval : 0;
+    if (h == 0) {
+      sc(0, row) = qs;
+      sc(1, row) = l;
+      sc(2, row) = u;
+      sc(3, row) = cb;
+      sc(6, row) = isx ? D : E;
+      sc(7, row) = E;
+      set_rho(st.rho);
+    }
+    if (tid == 0) {
+      CD[0] = cscale;
+      CD[1] = 1.0 / cscale;
+      CD[2] = st.rho;
+      CD[3] = CD[4] = 0.0;
+      CI[0] = -10;
+      CI[1] = 0;
+      CI[2] = 1;
+      CI[3] = chk_iv ? chk_iv : 0x7fffffff;
+      CI[4] = ada_iv ? ada_iv : 0x7fffffff;
+      CI[5] = 1;
+      CI[6] = 0;
+    }
+    __syncthreads();
+    // ---- iterations ------------------------------------------------------------------------------------------------------
+    const double alpha = st.alpha, sigma = st.sigma, oma = 1.0 - st.alpha;
+    for (;;) {
+      if (CI[6]) break;
+      int iter = CI[1];
+      if (CI[5]) {
+        factor(sigma);
+        if (h == 0) uv[((iter + 1) & 1) * US + row] = rhs_entry(sigma);  // the buffer iteration iter+1 reads
+        __syncthreads();
+      }
+      if (iter >= st.max_iter) break;
+      // plain iterations up to the next one that needs residuals: a tight loop with nothing but the solve and the update
+      const int next_chk = CI[3], next_ada = CI[4];
+      const int next_special = min(min(next_chk, next_ada), st.max_iter);
+      {
+        const double* ub_ = uv + ((iter + 1) & 1) * US;
+        double* un = uv + (iter & 1) * US;
+#pragma unroll 1
+        for (int k = next_special - iter - 1; k > 0; k--) {
+          update_row(-tile_dot(ub_), alpha, oma);
+          if (h == 0) un[row] = rhs_entry(sigma);
+          __syncthreads();
+          const double* tmp = ub_;
+          ub_ = un;
+          un = const_cast<double*>(tmp);
+        }
+      }
+      // the special iteration: same update, then residuals
+      iter = next_special;
+      const bool check = iter == next_chk, adapt = iter == next_ada;
+      if (h == 0) {
+        sc(9, row) = x;
+        sc(10, row) = y;
+      }
+      update_row(-tile_dot(uv + (iter & 1) * US), alpha, oma);
+      if (h == 0) {
+        uv[((iter + 1) & 1) * US + row] = rhs_entry(sigma);
+        cv[row] = isx ? x : 0.0;
+        cv[NP + row] = isg ? y : 0.0;
+      }
+      __syncthreads();
+      // ---- residuals ------------------------------------------------------------------------------
+      const double dx = x - sc(9, row), dy = y - sc(10, row);
+      const double D_ = sc(6, row), E_ = hasbox ? sc(7, row) : D_;  // D: x rows; E: the owned constraint row
+      const double qs_ = sc(0, row), cbv = sc(3, row), lo = sc(1, row), up = sc(2, row);
+      const double cscale_ = CD[0], cinv = CD[1];
+      double rho0 = CD[2];
+      double px, py;
+      k0_products(cv, cv + NP, px, py);
+      double* rbuf = red + 2 * (REG_MAXW * 16);
+      double pdy = 0.0;  // delta_y projected on the polar of the recession cone (primal infeasibility certificate)
+      {
+        const double ax = hasc ? (isg ? px : cbv * x) : 0.0;
+        const double einv = hasc ? 1.0 / E_ : 0.0;
+        const double zz = hasc ? z : 0.0;
+        const double r = ax - zz;
+        red_put<true>(rbuf, 0, fabs(einv * r));
+        red_put<true>(rbuf, 1, fabs(r));
+        red_put<true>(rbuf, 2, fabs(einv * zz));
+        red_put<true>(rbuf, 3, fabs(einv * ax));
+        red_put<true>(rbuf, 4, fabs(zz));
+        red_put<true>(rbuf, 5, fabs(ax));
+        if (hasc) {
+          pdy = dy;
+          if (up > QPC_INFTY * QPC_MIN_SCALING) pdy = (lo < -QPC_INFTY * QPC_MIN_SCALING) ? 0.0 : fmin(pdy, 0.0);
+          else if (lo < -QPC_INFTY * QPC_MIN_SCALING) pdy = fmax(pdy, 0.0);
+        }
+        red_put<true>(rbuf, 11, fabs(E_ * pdy));
+        red_put<false>(rbuf, 13, (hasc && h == 0) ? up * fmax(pdy, 0.0) + lo * fmin(pdy, 0.0) : 0.0);
+      }
+      {
+        const double aty = isx ? py + (hasbox ? cbv * y : 0.0) : 0.0;
+        const double dinv = isx ? 1.0 / D_ : 0.0;
+        const double pxx = isx ? px : 0.0, qq = isx ? qs_ : 0.0;
+        const double r = pxx + qq + aty;
+        const double big = fmax(fabs(qq), fmax(fabs(aty), fabs(pxx)));
+        red_put<true>(rbuf, 6, fabs(dinv * r));
+        red_put<true>(rbuf, 7, fabs(r));
+        red_put<true>(rbuf, 8, dinv * big);
+        red_put<true>(rbuf, 9, big);
+        red_put<true>(rbuf, 10, (isx && !finite_val(x)) ? 1.0 : 0.0);
+        red_put<true>(rbuf, 12, isx ? fabs(D_ * dx) : 0.0);
+        red_put<false>(rbuf, 14, (isx && h == 0) ? qs_ * dx : 0.0);
+      }
+      __syncthreads();
+      auto MX = [&](int k) { return red_get<true>(rbuf, k); };
+      auto SM = [&](int k) { return red_get<false>(rbuf, k); };
+      const double pri_res = MX(0), dua_res = cinv * MX(6);
+      int status = -10;
+      bool done = false, refactor = false;
+      if (MX(10) != 0.0 || !finite_val(pri_res) || !finite_val(dua_res)) {
+        status = -8;
+        done = true;
+      }
+      if (!done && (check || iter == st.max_iter)) {
+        for (int pass = 0; pass < 2 && !done; pass++) {
+          if (pass == 1 && iter != st.max_iter) break;  // the 10x relaxed test only applies at the iteration limit
+          const double f = pass ? 10.0 : 1.0;
+          const double eps_abs = f * st.eps_abs, eps_rel = f * st.eps_rel;
+          const double epi = f * st.eps_prim_inf, edi = f * st.eps_dual_inf;
+          const bool prim_ok = m == 0 || pri_res < eps_abs + eps_rel * fmax(MX(2), MX(3));
+          const bool dual_ok = dua_res < eps_abs + eps_rel * cinv * MX(8);
+          if (prim_ok && dual_ok) {
+            status = pass ? 2 : 1;
+            done = true;
+            break;
+          }
+          const double ndy = MX(11), ndx = MX(12);
+          if (!prim_ok && ndy > epi && SM(13) < -epi * ndy) {
+            // primal infeasibility: |D^-1 A' dy|_inf < eps |E dy|_inf
+            if (h == 0) {
+              cv[row] = 0.0;
+              cv[NP + row] = isg ? pdy : 0.0;
+            }
+            __syncthreads();
+            double qx, qy;
+            k0_products(cv, cv + NP, qx, qy);
+            double na[1];
+            na[0] = isx ? fabs((qy + (hasbox ? cbv * pdy : 0.0)) / D_) : 0.0;
+            reg_block_reduce<1, 0>(na, red, redsel);
+            if (na[0] < epi * ndy) {
+              status = pass ? 3 : -3;
+              done = true;
+              break;
+            }
+          }
+          if (!dual_ok && ndx > edi && SM(14) < -cscale_ * edi * ndx) {
+            // dual infeasibility: |D^-1 P dx|_inf small and A dx inside the recession cone of [l, u]
+            if (h == 0) {
+              cv[row] = isx ? dx : 0.0;
+              cv[NP + row] = 0.0;
+            }
+            __syncthreads();
+            double qx, qy;
+            k0_products(cv, cv + NP, qx, qy);
+            double nb2[2];
+            nb2[0] = isx ? fabs(qx / D_) : 0.0;
+            nb2[1] = 0.0;
+            if (hasc) {
+              const double adx = (isg ? qx : cbv * dx) / E_;
+              if ((up < QPC_INFTY * QPC_MIN_SCALING && adx > edi * ndx) ||
+                  (lo > -QPC_INFTY * QPC_MIN_SCALING && adx < -edi * ndx))
+                nb2[1] = 1.0;
+            }
+            reg_block_reduce<2, 0>(nb2, red, redsel);
+            if (nb2[0] < cscale_ * edi * ndx && nb2[1] == 0.0) {
+              status = pass ? 4 : -4;
+              done = true;
+              break;
+            }
+          }
+        }
+        if (!done && iter == st.max_iter) {
+          status = -2;
+          done = true;
+        }
+      }
+      if (!done && adapt) {
+        // rho <- rho sqrt( (r_p / max(|Ax|,|z|)) / (r_d / max(|Px|,|A'y|,|q|)) ) on scaled quantities (B.3 step 6)
+        const double pr = MX(1) / (fmax(MX(4), MX(5)) + 1e-10);
+        const double dr = MX(7) / (MX(9) + 1e-10);
+        double rho_new = rho0 * sqrt(pr / (dr + 1e-10));
+        rho_new = fmin(fmax(rho_new, QPC_RHO_MIN), QPC_RHO_MAX);
+        if (rho_new > rho0 * st.adaptive_rho_tolerance || rho_new < rho0 / st.adaptive_rho_tolerance) {
+          rho0 = rho_new;
+          if (h == 0) set_rho(rho0);
+          refactor = true;
+        }
+      }
+      if (tid == 0) {
+        CD[2] = rho0;
+        CD[3] = pri_res;
+        CD[4] = dua_res;
+        CI[0] = status;
+        CI[1] = iter;
+        if (refactor) CI[2] += 1;
+        if (check) CI[3] = next_chk + chk_iv;
+        if (adapt) CI[4] = next_ada + ada_iv;
+        CI[5] = refactor ? 1 : 0;
+        CI[6] = done ? 1 : 0;
+      }
+      __syncthreads();
+    }
+    // ---- unscale and store -----------------------------------------------------------------------------------------------
+    if (h == 0) {
+      const double cinv = CD[1];
+      if (isx) pb_.x[xi] = sc(6, row) * x;
+      if (pb_.y) {
+        if (isg) pb_.y[row] = cinv * sc(6, row) * y;
+        if (hasbox) pb_.y[mg + xi - (n - nbx)] = cinv * sc(7, row) * y;
+      }
+    }
+    if (tid == 0) {
+      *pb_.status = CI[0];
+      if (pb_.iters) *pb_.iters = CI[1];
+      if (pb_.nfac) *pb_.nfac = CI[2];
+      if (pb_.res) {
+        pb_.res[0] = CD[3];
+        pb_.res[1] = CD[4];
+      }
+    }
+    __syncthreads();
+  }
+};
+
+#endif  // __CUDACC__
+
+}  // namespace qpc

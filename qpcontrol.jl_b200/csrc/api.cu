@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -31,6 +32,7 @@ struct Backend {
 };
 
 #include "admm.cuh"
+#include "admm_reg.cuh"
 #include "kin.cuh"
 #include "setup_api.h"
 
@@ -85,6 +87,45 @@ qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B) 
     pb.res = qb.res ? qb.res + 2 * inst : nullptr;
     pb.nfac = qb.nfac ? qb.nfac + inst : nullptr;
     admm_solve(st, pb, n, mg, nbx, smem);
+  }
+}
+
+// register-resident variant (admm_reg.cuh): TC = tile columns per thread, 8 TC >= n + mg
+template <int C>
+struct RegTraits {
+  static constexpr int MAXT = 16 * C;
+  // registers per thread chosen so that the intended number of CTAs per SM fits the 64K-register file with the
+  // per-warp allocation granularity: 128 -> 3 CTAs of 160 threads (TC = 10), 4 of 128 (TC = 8); larger tiles run
+  // 2 or 1 CTA per SM
+#ifndef QPC_REGS10
+#define QPC_REGS10 128
+#endif
+  static constexpr int MAXREG = C <= 8 ? 128 : (C <= 10 ? QPC_REGS10 : (C <= 12 ? 168 : (C <= 16 ? 255 : 224)));
+};
+template <int C>
+__global__ void __launch_bounds__(RegTraits<C>::MAXT) __maxnreg__(RegTraits<C>::MAXREG)
+qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B) {
+  extern __shared__ double smem[];
+  for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    AdmmProblem pb;
+    pb.P = qb.P + inst * n * n;
+    pb.qv = qb.qv + inst * n;
+    pb.G = qb.G + inst * mg * n;
+    pb.lg = qb.lg + inst * mg;
+    pb.ug = qb.ug + inst * mg;
+    pb.lb = qb.lb + inst * nbx;
+    pb.ub = qb.ub + inst * nbx;
+    pb.x = qb.x + inst * n;
+    pb.y = qb.y ? qb.y + inst * (mg + nbx) : nullptr;
+    pb.status = qb.status + inst;
+    pb.iters = qb.iters ? qb.iters + inst : nullptr;
+    pb.res = qb.res ? qb.res + 2 * inst : nullptr;
+    pb.nfac = qb.nfac ? qb.nfac + inst : nullptr;
+    RegSolver<C> s;
+    s.n = n;
+    s.mg = mg;
+    s.nbx = nbx;
+    s.solve(st, pb, smem);
   }
 }
 
@@ -171,14 +212,65 @@ static int upload_program(qpc_controller* c) {
   return QPC_OK;
 }
 
+static int launch_grid(long long B) { return (int)(B < (1ll << 30) ? B : (1ll << 30)); }
+
+// ---- ADMM dispatch: register-resident kernel when the KKT matrix fits the register file, shared-memory kernel otherwise
+static int reg_columns(int NK) {
+  static const int sizes[] = {2, 4, 6, 8, 10, 12, 14, 16, 18};
+  const char* e = getenv("QPC_ADMM_SMEM");
+  if (e && e[0] == '1') return 0;
+  for (int c : sizes)
+    if (admm_reg_positions(c) >= NK) return c;
+  return 0;
+}
+template <int C>
+static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long B,
+                              cudaStream_t stream) {
+  const int NT = admm_reg_threads(C);
+  const int bytes = admm_reg_smem_doubles(C) * 8;
+  static int configured[64] = {0};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && configured[dev] < bytes) {
+    cudaError_t e = cudaFuncSetAttribute(qpc_admm_reg_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(qpc_admm_reg_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    configured[dev] = bytes;
+  }
+  qpc_admm_reg_kernel<C><<<launch_grid(B), NT, bytes, stream>>>(st, qb, n, mg, nbx, B);
+  return cudaGetLastError();
+}
+// returns cudaSuccess or the launch error; `smem_configured` = the v1 kernel's attribute was already set for this size
+static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long B,
+                               cudaStream_t stream) {
+  switch (reg_columns(n + mg)) {
+    case 2: return launch_reg<2>(st, qb, n, mg, nbx, B, stream);
+    case 4: return launch_reg<4>(st, qb, n, mg, nbx, B, stream);
+    case 6: return launch_reg<6>(st, qb, n, mg, nbx, B, stream);
+    case 8: return launch_reg<8>(st, qb, n, mg, nbx, B, stream);
+    case 10: return launch_reg<10>(st, qb, n, mg, nbx, B, stream);
+    case 12: return launch_reg<12>(st, qb, n, mg, nbx, B, stream);
+    case 14: return launch_reg<14>(st, qb, n, mg, nbx, B, stream);
+    case 16: return launch_reg<16>(st, qb, n, mg, nbx, B, stream);
+    case 18: return launch_reg<18>(st, qb, n, mg, nbx, B, stream);
+    default: break;
+  }
+  const int asmem = admm_smem_doubles(n, mg, nbx) * 8;
+  qpc_admm_kernel<<<launch_grid(B), ADMM_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, B);
+  return cudaGetLastError();
+}
+
 static int configure_kernels(const DevProgram& p) {
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
   const int asmem = admm_smem_doubles(p.n, p.mg, p.nbx) * 8;
-  if (ksm > 227 * 1024 || asmem > 227 * 1024)
+  if (ksm > 227 * 1024 || (asmem > 227 * 1024 && !reg_columns(p.n + p.mg)))
     return qpc_fail(QPC_ERR_LIMIT, "problem does not fit the 227 KB shared memory of one CTA");
   CUDA_TRY(cudaFuncSetAttribute(qpc_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
   CUDA_TRY(cudaFuncSetAttribute(qpc_inverse_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
-  CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
+  if (asmem <= 227 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
   return QPC_OK;
 }
 
@@ -200,8 +292,6 @@ static QpBuffers qp_view(const DeviceBuffers& b) {
   return q;
 }
 
-static int launch_grid(long long B) { return (int)(B < (1ll << 30) ? B : (1ll << 30)); }
-
 // the tick on device pointers; asynchronous on `stream`
 static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* tau, double* vdot, double* wrench,
                     int* status, int* iters, double* res, int* nfac, cudaStream_t stream) {
@@ -214,13 +304,12 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
   qb.nfac = nfac ? nfac : c->be.d_nfac;
   const bool prof = c->be.profiling;
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
-  const int asmem = admm_smem_doubles(p.n, p.mg, p.nbx) * 8;
   const int grid = launch_grid(B);
   if (prof) cudaEventRecord(c->be.ev[0], stream);
   qpc_assemble_kernel<<<grid, ASM_THREADS, ksm, stream>>>(dp, io, qb, B);
   if (prof) cudaEventRecord(c->be.ev[1], stream);
   if (p.n > 0)
-    qpc_admm_kernel<<<grid, ADMM_THREADS, asmem, stream>>>(p.settings, qb, p.n, p.mg, p.nbx, B);
+    CUDA_TRY(launch_admm(p.settings, qb, p.n, p.mg, p.nbx, B, stream));
   else
     qpc_trivial_status_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(qb.status, qb.iters, qb.res, B);
   if (prof) cudaEventRecord(c->be.ev[2], stream);
@@ -503,9 +592,11 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
   Settings s;
   qpc_copy_settings(st, s);
   const int asmem = admm_smem_doubles(n, mg, nbox) * 8;
-  if (asmem > 227 * 1024) return qpc_fail(QPC_ERR_LIMIT, "QP does not fit the 227 KB shared memory of one CTA");
+  if (asmem > 227 * 1024 && !reg_columns(n + mg))
+    return qpc_fail(QPC_ERR_LIMIT, "QP fits neither the register file nor the 227 KB shared memory of one CTA");
   CUDA_TRY(cudaSetDevice(device));
-  CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
+  if (asmem <= 227 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
   QpBuffers qb;
   memset(&qb, 0, sizeof(qb));
   if (flags == QPC_DEVICE_PTRS) {
@@ -521,8 +612,7 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
     qb.status = status;
     qb.iters = iters;
     qb.res = residuals;
-    qpc_admm_kernel<<<launch_grid(B), ADMM_THREADS, asmem, (cudaStream_t)stream_>>>(s, qb, n, mg, nbox, B);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_admm(s, qb, n, mg, nbox, B, (cudaStream_t)stream_));
     return QPC_OK;
   }
   // host pointers: temporary device copies (this entry point serves the synthetic-QP sweep, not the control tick)
@@ -550,8 +640,7 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
     }
     qb.status = dstat;
     qb.iters = diter;
-    qpc_admm_kernel<<<launch_grid(B), ADMM_THREADS, asmem>>>(s, qb, n, mg, nbox, B);
-    if ((e = cudaGetLastError()) || (e = cudaDeviceSynchronize()) ||
+    if ((e = launch_admm(s, qb, n, mg, nbox, B, nullptr)) || (e = cudaDeviceSynchronize()) ||
         (e = cudaMemcpy(x, qb.x, sizeof(double) * B * n, cudaMemcpyDeviceToHost)) ||
         (y && (e = cudaMemcpy(y, qb.y, sizeof(double) * B * m, cudaMemcpyDeviceToHost))) ||
         (e = cudaMemcpy(status, dstat, sizeof(int) * B, cudaMemcpyDeviceToHost)) ||
