@@ -169,7 +169,11 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
-    rank, world, local = _env_int("RANK", 0), _env_int("WORLD_SIZE", 1), _env_int("LOCAL_RANK", 0)
+    import qpc_loader
+    from importlib import import_module
+    qpc_loader.load()
+    sharding = import_module("qpcontrol_jl_b200.sharding")
+    rank, world, local = sharding.env_rank_world()
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -180,8 +184,7 @@ def main():
                          "CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import qpc_loader
+        sharding.init_process_group("nccl", local)
     qpc = qpc_loader.load()
     from qpcontrol_jl_b200 import _lib
 
@@ -218,9 +221,7 @@ def main():
         dev.solve_device(B, dq, dv, out, contact_weight=dcw, contact_maxnormalforce=dcm, stream=stream.cuda_stream)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        sharding.barrier(cuda)
 
     # ---- device-resident throughput ("value") -----------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -290,10 +291,7 @@ def main():
     e2e_ok = float(np.mean((hres.status == 1) | (hres.status == 2)))
 
     # ---- max over ranks -----------------------------------------------------------------------------------------------------
-    t = torch.tensor([ms_total, e2e_s, stage[1]], dtype=torch.float64, device=cuda)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max, e2e_s_max, admm_ms = [float(x) for x in t.cpu()]
+    ms_total_max, e2e_s_max, admm_ms = [float(x) for x in sharding.max_over_ranks([ms_total, e2e_s, stage[1]], cuda)]
     total_solves = B * world * args.steps
     value = total_solves / (ms_total_max * 1e-3)
     e2e_value = total_solves / e2e_s_max

@@ -12,4 +12,4 @@ from .program import (ANGULAR, HARD, JOINT, LINEAR, LINEAR_MOMENTUM_RATE, MATRIX
                       OSQPSettings, PointAccelerationTask, Program, QPSolveFailure, SpatialAccelerationTask,
                       checkstatus)
 from .controller import BatchResult, MomentumBasedController, StandingController, center_of_mass_host
-from . import scenarios
+from . import scenarios, sharding

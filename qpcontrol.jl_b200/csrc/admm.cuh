@@ -34,16 +34,19 @@ struct AdmmSmem {
   double *red;                                    // reduction scratch: 32 warps x 16
   double *sc;                                     // scalars
 };
-QPC_HD int admm_smem_doubles(int n, int mg, int nbx) {
+QPC_HD int admm_matrix_doubles(int n, int mg) { return n * n + 2 * mg * n; }
+QPC_HD int admm_vector_doubles(int n, int mg, int nbx) {
   const int m = mg + nbx;
-  return n * n + 2 * mg * n + 7 * n + 9 * m + nbx + 32 * 16 + 32 + 8;
+  return 7 * n + 9 * m + nbx + 32 * 16 + 32 + 8;
 }
-QPC_HD AdmmSmem admm_layout(double* b, int n, int mg, int nbx) {
+QPC_HD int admm_smem_doubles(int n, int mg, int nbx) { return admm_matrix_doubles(n, mg) + admm_vector_doubles(n, mg, nbx); }
+// `mat` holds the three matrices (shared memory, or a per-CTA global scratch for QPs that do not fit), `b` the vectors
+QPC_HD AdmmSmem admm_layout(double* mat, double* b, int n, int mg, int nbx) {
   const int m = mg + nbx;
   AdmmSmem s;
-  s.M = b;    b += n * n;
-  s.Gs = b;   b += mg * n;
-  s.Gt = b;   b += mg * n;
+  s.M = mat;
+  s.Gs = mat + n * n;
+  s.Gt = s.Gs + mg * n;
   s.D = b;    b += n;
   s.qs = b;   b += n;
   s.x = b;    b += n;
@@ -252,11 +255,13 @@ QPC_DEV void admm_factor(const AdmmSmem& s, const double* __restrict__ P, int n,
   QPC_SYNC();
 }
 
-// The solver.  `smem` must hold admm_smem_doubles(n, mg, nbx) doubles.
-QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg, int nbx, double* smem) {
+// The solver.  `smem` must hold admm_smem_doubles(n, mg, nbx) doubles, or only admm_vector_doubles when `gmat`
+// (admm_matrix_doubles of global scratch owned by this CTA) is given.
+QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg, int nbx, double* smem,
+                        double* gmat = nullptr) {
   const int tid = QPC_TID, nt = QPC_NT;
   const int m = mg + nbx, nx0 = n - nbx;
-  AdmmSmem s = admm_layout(smem, n, mg, nbx);
+  AdmmSmem s = gmat ? admm_layout(gmat, smem, n, mg, nbx) : admm_layout(smem, smem + admm_matrix_doubles(n, mg), n, mg, nbx);
   // ---- load ------------------------------------------------------------------------------------------------------
   for (int k = tid; k < n * n; k += nt) s.M[k] = pb.P[k];
   for (int k = tid; k < mg * n; k += nt) {

@@ -37,7 +37,7 @@ QPC_HD int admm_reg_positions(int TC) { return REG_NB * TC; }
 QPC_HD int admm_reg_threads(int TC) { return 2 * REG_NB * TC; }  // (NP / 4 row groups) x 8 column blocks
 QPC_HD int admm_reg_smem_doubles(int TC) {
   const int NP = REG_NB * TC;
-  return REG_TR * TC * admm_reg_threads(TC) + 2 * (NP + 2) + 2 * NP + 3 * REG_MAXW * 16 + 13 * NP + 16;
+  return REG_TR * TC * admm_reg_threads(TC) + 2 * (2 * NP + 2) + 2 * NP + 3 * REG_MAXW * 16 + 13 * NP + 16;
 }
 
 #if defined(__CUDACC__)
@@ -111,7 +111,8 @@ struct RegSolver {
   static constexpr int NP = REG_NB * TC;      // row / column positions: general rows (mg), x rows (n), padding
   static constexpr int NT = 2 * REG_NB * TC;  // threads
   static constexpr int TR = REG_TR;
-  static constexpr int US = NP + 2;           // stride of the double-buffered vectors
+  static constexpr int US = NP + 2;           // stride of the double-buffered iteration vectors
+  static constexpr int PS = 2 * NP + 2;       // stride of the double-buffered published pivot rows (same storage)
   // ---- geometry -------------------------------------------------------------------------------------------------
   int n, mg, nbx, NK, tid, q, g, row, h, c0;  // q: column block, g: row group, row: the row this lane owns
   bool isx, isg, hasbox, hasc;  // x-row / general-constraint row / x-row that also owns a box row / owns any row
@@ -153,6 +154,11 @@ struct RegSolver {
       const double cb = sc(3, row), rho = sc(4, row), rinv = sc(5, row);
       sc(8, row) = isx ? sigma + (hasbox ? rho * cb * cb : 0.0) : (isg ? -rinv : 1.0);
     }
+    // the row state is dead weight during the sweep: park it in the (idle) check vector and xprev / yprev slots
+    // the row state is per row (both lanes of a pair hold the same values)
+    cv[row] = z;
+    sc(9, row) = y;
+    sc(10, row) = x;
     load_tile();
     __syncthreads();
 #pragma unroll
@@ -163,40 +169,52 @@ struct RegSolver {
       for (int c = 0; c < TC; c++)
         if (c == ck) a[r][c] += dd;
     }
-    double* pb = uv;  // 2 x (NP + 2): published pivot row (raw register dump of the 8 column blocks), then 1/pivot
-    if (g == 0) {
-      double2* pw = reinterpret_cast<double2*>(pb + c0);
+    // Published pivot row, double-buffered, PS doubles each: [0, NP) the raw register dump of the 8 column blocks (what
+    // the DFMAs consume, in the current rotation), [NP, 2 NP) the same row in canonical column order (entry j is, by
+    // symmetry, the multiplier of row j), [2 NP] 1 / pivot.
+    double* pb = uv;
+    auto publish = [&](double* pw, const double (&rowv)[TC], int sm1, bool pivot_lane) {
+      double2* pw2 = reinterpret_cast<double2*>(pw + c0);
 #pragma unroll
-      for (int c = 0; c < TC / 2; c++) pw[c] = make_double2(a[0][2 * c], a[0][2 * c + 1]);
-      if (q == 0) pb[NP] = 1.0 / a[0][0];
-    }
+      for (int c = 0; c < TC / 2; c++) pw2[c] = make_double2(rowv[2 * c], rowv[2 * c + 1]);
+#pragma unroll
+      for (int c = 0; c < TC; c++) {
+        int idx = c + sm1;
+        idx -= idx >= TC ? TC : 0;
+        pw[NP + c0 + idx] = rowv[c];
+      }
+      if (pivot_lane) pw[2 * NP] = 1.0 / rowv[0];
+    };
+    if (g == 0) publish(pb, a[0], 0, q == 0);
     __syncthreads();
     for (int s4 = 0; s4 < NP / 4; s4++) {
+      const bool own = g == s4;
 #pragma unroll
       for (int rr = 0; rr < TR; rr++) {
         const int s = 4 * s4 + rr;
-        const double* pr = pb + (s & 1) * US;
-        const int b = s / TC, sm = s - b * TC;  // pivot column block and rotation count (mod TC)
-        const double dinv = pr[NP];
-        const double2* p2 = reinterpret_cast<const double2*>(pr + c0);
+        const double* pr = pb + (s & 1) * PS;
+        const int b = s / TC;  // pivot column block
+        const double dinv = pr[2 * NP];
         double f[TR];
-#pragma unroll
-        for (int r = 0; r < TR; r++) {
-          const int pos = 4 * g + r, blk = pos / TC;
-          int ci = pos - blk * TC - sm;
-          ci += ci < 0 ? TC : 0;
-          f[r] = pr[blk * TC + ci] * dinv;
+        {
+          const double2* f2 = reinterpret_cast<const double2*>(pr + NP + 4 * g);
+          const double2 fa = f2[0], fb = f2[1];
+          f[0] = fa.x * dinv;
+          f[1] = fa.y * dinv;
+          f[2] = fb.x * dinv;
+          f[3] = fb.y * dinv;
         }
         const bool inb = q == b;
-        const bool own = g == s4;
+        const double2* p2 = reinterpret_cast<const double2*>(pr + c0);
         double t0[TR];
 #pragma unroll
         for (int r = 0; r < TR; r++) t0[r] = a[r][0];
-        const double p0 = pr[c0];
+        double p0 = 0.0;
         // a[r][c-1] <- a[r][c] - f[r] p[c]  (the pivot row itself: a[r][c] / pivot), two columns per 16-byte load
 #pragma unroll
         for (int c2 = 0; c2 < TC / 2; c2++) {
           const double2 v = p2[c2];
+          if (c2 == 0) p0 = v.x;
 #pragma unroll
           for (int r = 0; r < TR; r++) {
             if (r == rr && own) {
@@ -218,15 +236,15 @@ struct RegSolver {
         constexpr int TRm = TR - 1;
         const int rn = (rr + 1) & TRm;
         if (s1 < NP && g == (s1 >> 2)) {
-          double* pw = pb + (s1 & 1) * US;
-          double2* pw2 = reinterpret_cast<double2*>(pw + c0);
-#pragma unroll
-          for (int c = 0; c < TC / 2; c++) pw2[c] = make_double2(a[rn][2 * c], a[rn][2 * c + 1]);
-          if (q == s1 / TC) pw[NP] = 1.0 / a[rn][0];
+          const int b1 = s1 / TC;
+          publish(pb + (s1 & 1) * PS, a[rn], s1 - b1 * TC, q == b1);
         }
         __syncthreads();
       }
     }
+    z = cv[row];
+    y = sc(9, row);
+    x = sc(10, row);
   }
 
   // right-hand side entry of the owned row for the next KKT solve; w = z - y / rho
@@ -274,23 +292,23 @@ struct RegSolver {
     return group_reduce<false>(s0, q);
   }
 
-  // products of the owned row of the scaled, unswept matrix: x-rows get (P vx, G' vy), general rows get (G vx, 0)
-  __device__ __forceinline__ void k0_products(const double* vx, const double* vy, double& px, double& py) const {
-    double s0[TR], s1[TR];
+  // product of the owned row of the scaled, unswept matrix with a vector in shared memory
+  __device__ __forceinline__ double k0_product(const double* v) const {
+    double s0[TR];
 #pragma unroll
-    for (int r = 0; r < TR; r++) s0[r] = s1[r] = 0.0;
+    for (int r = 0; r < TR; r++) s0[r] = 0.0;
 #pragma unroll
     for (int c = 0; c < TC; c++) {
-      const double ex = vx[c0 + c], ey = vy[c0 + c];
+      const double e = v[c0 + c];
 #pragma unroll
-      for (int r = 0; r < TR; r++) {
-        const double m = K0[(r * TC + c) * NT + tid];
-        s0[r] = fma(m, ex, s0[r]);
-        s1[r] = fma(m, ey, s1[r]);
-      }
+      for (int r = 0; r < TR; r++) s0[r] = fma(K0[(r * TC + c) * NT + tid], e, s0[r]);
     }
-    px = group_reduce<false>(s0, q);
-    py = group_reduce<false>(s1, q);
+    return group_reduce<false>(s0, q);
+  }
+  // x-rows get (P vx, G' vy), general rows get (G vx, 0)
+  __device__ __forceinline__ void k0_products(const double* vx, const double* vy, double& px, double& py) const {
+    px = k0_product(vx);
+    py = k0_product(vy);
   }
 
   __device__ void solve(const Settings& st, const AdmmProblem& pb_, double* smem) {
@@ -307,15 +325,15 @@ struct RegSolver {
     hasbox = isx && xi >= n - nbx;
     hasc = hasbox || isg;
     K0 = smem;
-    uv = K0 + TR * TC * NT;        // 2 x (NP + 2)
-    cv = uv + 2 * US;              // 2 x NP
+    uv = K0 + TR * TC * NT;        // 2 x PS (sweep) overlaid by 2 x US (iterations)
+    cv = uv + 2 * PS;              // 2 x NP
     red = cv + 2 * NP;             // 3 x REG_MAXW x 16 (two alternating buffers + the residual check's own)
     SC = red + 3 * REG_MAXW * 16;  // 13 x NP
     redsel = 0;
     const int m = mg + nbx;
     // ---- load: coalesced global reads, scattered into the thread-major staging area ----------------------------------
     for (int k = tid; k < TR * TC * NT; k += NT) K0[k] = 0.0;
-    for (int k = tid; k < 2 * US + 2 * NP; k += NT) uv[k] = 0.0;
+    for (int k = tid; k < 2 * PS + 2 * NP; k += NT) uv[k] = 0.0;
     __syncthreads();
     auto k0_index = [&](int i, int j) {  // element (row position i, column position j)
       const int qq = j / TC;

@@ -38,11 +38,12 @@ struct Backend {
 
 using namespace qpc;
 
+static thread_local std::string g_launch_note;  // resource figures of the last failed kernel launch
 #define CUDA_TRY(expr)                                                                                  \
   do {                                                                                                  \
     cudaError_t e__ = (expr);                                                                           \
     if (e__ != cudaSuccess)                                                                             \
-      return qpc_fail(QPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));               \
+      return qpc_fail(QPC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__) + g_launch_note); \
   } while (0)
 
 // ---- kernels: one robot instance / one QP per CTA ----------------------------------------------------------------------
@@ -69,8 +70,9 @@ qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb,
 }
 
 __global__ void __launch_bounds__(ADMM_THREADS)
-qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B) {
+qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B, double* gscratch) {
   extern __shared__ double smem[];
+  double* gmat = gscratch ? gscratch + (size_t)blockIdx.x * admm_matrix_doubles(n, mg) : nullptr;
   for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
     AdmmProblem pb;
     pb.P = qb.P + inst * n * n;
@@ -86,7 +88,7 @@ qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B) 
     pb.iters = qb.iters ? qb.iters + inst : nullptr;
     pb.res = qb.res ? qb.res + 2 * inst : nullptr;
     pb.nfac = qb.nfac ? qb.nfac + inst : nullptr;
-    admm_solve(st, pb, n, mg, nbx, smem);
+    admm_solve(st, pb, n, mg, nbx, smem, gmat);
   }
 }
 
@@ -100,7 +102,7 @@ struct RegTraits {
 #ifndef QPC_REGS10
 #define QPC_REGS10 128
 #endif
-  static constexpr int MAXREG = C <= 8 ? 128 : (C <= 10 ? QPC_REGS10 : (C <= 12 ? 168 : (C <= 16 ? 255 : 224)));
+  static constexpr int MAXREG = C <= 8 ? 128 : (C <= 10 ? QPC_REGS10 : (C <= 12 ? 168 : (C <= 14 ? 255 : (C <= 16 ? 240 : 200))));
 };
 template <int C>
 __global__ void __launch_bounds__(RegTraits<C>::MAXT) __maxnreg__(RegTraits<C>::MAXREG)
@@ -240,33 +242,62 @@ static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, in
     configured[dev] = bytes;
   }
   qpc_admm_reg_kernel<C><<<launch_grid(B), NT, bytes, stream>>>(st, qb, n, mg, nbx, B);
-  return cudaGetLastError();
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, qpc_admm_reg_kernel<C>) == cudaSuccess)
+      g_launch_note = " [admm_reg TC=" + std::to_string(C) + " threads=" + std::to_string(NT) + " regs=" +
+                      std::to_string(fa.numRegs) + " dyn_smem=" + std::to_string(bytes) + " static_smem=" +
+                      std::to_string(fa.sharedSizeBytes) + " local=" + std::to_string(fa.localSizeBytes) + "]";
+  }
+  return le;
 }
 // returns cudaSuccess or the launch error; `smem_configured` = the v1 kernel's attribute was already set for this size
 static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long B,
                                cudaStream_t stream) {
   switch (reg_columns(n + mg)) {
+#ifndef QPC_ONLY_TC10  /* development builds (register-liveness dumps) instantiate the Atlas tile only */
     case 2: return launch_reg<2>(st, qb, n, mg, nbx, B, stream);
     case 4: return launch_reg<4>(st, qb, n, mg, nbx, B, stream);
     case 6: return launch_reg<6>(st, qb, n, mg, nbx, B, stream);
     case 8: return launch_reg<8>(st, qb, n, mg, nbx, B, stream);
-    case 10: return launch_reg<10>(st, qb, n, mg, nbx, B, stream);
     case 12: return launch_reg<12>(st, qb, n, mg, nbx, B, stream);
     case 14: return launch_reg<14>(st, qb, n, mg, nbx, B, stream);
     case 16: return launch_reg<16>(st, qb, n, mg, nbx, B, stream);
     case 18: return launch_reg<18>(st, qb, n, mg, nbx, B, stream);
+#endif
+    case 10: return launch_reg<10>(st, qb, n, mg, nbx, B, stream);
     default: break;
   }
   const int asmem = admm_smem_doubles(n, mg, nbx) * 8;
-  qpc_admm_kernel<<<launch_grid(B), ADMM_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, B);
-  return cudaGetLastError();
+  if (asmem <= 227 * 1024) {
+    qpc_admm_kernel<<<launch_grid(B), ADMM_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, B, nullptr);
+    return cudaGetLastError();
+  }
+  // QPs that fit neither the register file nor shared memory: matrices in a per-CTA global scratch (L2 resident for
+  // the grid sizes used), vectors in shared memory; a bounded persistent grid strides over the batch
+  const int vsmem = admm_vector_doubles(n, mg, nbx) * 8;
+  if (vsmem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long grid = B < 2ll * sms ? B : 2ll * sms;
+  double* scratch = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)grid * admm_matrix_doubles(n, mg), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vsmem);
+  if (e == cudaSuccess) {
+    qpc_admm_kernel<<<(int)grid, ADMM_THREADS, vsmem, stream>>>(st, qb, n, mg, nbx, B, scratch);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(scratch, stream);
+  return e;
 }
 
 static int configure_kernels(const DevProgram& p) {
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
   const int asmem = admm_smem_doubles(p.n, p.mg, p.nbx) * 8;
-  if (ksm > 227 * 1024 || (asmem > 227 * 1024 && !reg_columns(p.n + p.mg)))
-    return qpc_fail(QPC_ERR_LIMIT, "problem does not fit the 227 KB shared memory of one CTA");
+  if (ksm > 227 * 1024) return qpc_fail(QPC_ERR_LIMIT, "mechanism does not fit the 227 KB shared memory of one CTA");
   CUDA_TRY(cudaFuncSetAttribute(qpc_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
   CUDA_TRY(cudaFuncSetAttribute(qpc_inverse_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
   if (asmem <= 227 * 1024)
@@ -592,8 +623,8 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
   Settings s;
   qpc_copy_settings(st, s);
   const int asmem = admm_smem_doubles(n, mg, nbox) * 8;
-  if (asmem > 227 * 1024 && !reg_columns(n + mg))
-    return qpc_fail(QPC_ERR_LIMIT, "QP fits neither the register file nor the 227 KB shared memory of one CTA");
+  if (admm_vector_doubles(n, mg, nbox) * 8 > 227 * 1024)
+    return qpc_fail(QPC_ERR_LIMIT, "QP vectors do not fit the 227 KB shared memory of one CTA");
   CUDA_TRY(cudaSetDevice(device));
   if (asmem <= 227 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));

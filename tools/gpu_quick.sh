@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-q}
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/${TAG}_pytest_gpu.log; echo "pytest rc=$?"
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -15 gpurun_out/${TAG}_pytest_gpu.log
 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 tail -c 600 gpurun_out/${TAG}_bench.err
