@@ -123,7 +123,7 @@ struct RegSolver {
   int redsel;
   // ---- registers: the tile and the state of the owned row -----------------------------------------------------------
   double a[TR][TC];
-  double x, z, y;
+  double x, z, yr;  // yr = y / rho of the owned constraint row: the iteration never needs y itself
 
   __device__ __forceinline__ double& sc(int k, int pos) const { return SC[k * NP + pos]; }
 
@@ -157,7 +157,7 @@ struct RegSolver {
     // the row state is dead weight during the sweep: park it in the (idle) check vector and xprev / yprev slots
     // the row state is per row (both lanes of a pair hold the same values)
     cv[row] = z;
-    sc(9, row) = y;
+    sc(9, row) = yr;
     sc(10, row) = x;
     load_tile();
     __syncthreads();
@@ -192,6 +192,16 @@ struct RegSolver {
 #pragma unroll
       for (int rr = 0; rr < TR; rr++) {
         const int s = 4 * s4 + rr;
+        if (s >= NK) {  // identity padding: the step is the bare rotation (multipliers are zero), no broadcast needed
+#pragma unroll
+          for (int r = 0; r < TR; r++) {
+            const double t0 = a[r][0];
+#pragma unroll
+            for (int c = 0; c < TC - 1; c++) a[r][c] = a[r][c + 1];
+            a[r][TC - 1] = t0;
+          }
+          continue;
+        }
         const double* pr = pb + (s & 1) * PS;
         const int b = s / TC;  // pivot column block
         const double dinv = pr[2 * NP];
@@ -235,7 +245,7 @@ struct RegSolver {
         const int s1 = s + 1;
         constexpr int TRm = TR - 1;
         const int rn = (rr + 1) & TRm;
-        if (s1 < NP && g == (s1 >> 2)) {
+        if (s1 < NK && g == (s1 >> 2)) {
           const int b1 = s1 / TC;
           publish(pb + (s1 & 1) * PS, a[rn], s1 - b1 * TC, q == b1);
         }
@@ -243,13 +253,14 @@ struct RegSolver {
       }
     }
     z = cv[row];
-    y = sc(9, row);
+    yr = sc(9, row);
     x = sc(10, row);
   }
 
-  // right-hand side entry of the owned row for the next KKT solve; w = z - y / rho
+  // right-hand side entry of the owned row for the next KKT solve: z - y/rho for a general row,
+  // sigma x - q + cb (rho z - y) for an x row (box term only if it owns one)
   __device__ __forceinline__ double rhs_entry(double sigma) const {
-    const double w = hasc ? fma(-y, sc(5, row), z) : 0.0;
+    const double w = hasc ? z - yr : 0.0;
     if (isg) return w;
     if (isx) return fma(sigma, x, -sc(0, row)) + (hasbox ? sc(12, row) * w : 0.0);
     return 0.0;
@@ -261,24 +272,12 @@ struct RegSolver {
     sc(12, row) = sc(3, row) * r;
   }
 
-  // one ADMM iteration of the owned row given the KKT solve result t, written so that the
-  // dependent chain after t is as short as possible
-  __device__ __forceinline__ void update_row(double t, double alpha, double oma) {
-    if (isx) x = fma(alpha, t, oma * x);
-    if (hasc) {
-      const double rinv = sc(5, row), rho = sc(4, row), lo = sc(1, row), up = sc(2, row);
-      const double zt = isg ? fma(t, rinv, fma(-y, rinv, z)) : sc(3, row) * t;  // z - y/rho does not wait for t
-      const double zr = fma(alpha, zt, oma * z);
-      double zn = fma(y, rinv, zr);
-      zn = zn < lo ? lo : zn;
-      zn = zn > up ? up : zn;
-      y = fma(rho, zr - zn, y);
-      z = zn;
-    }
-  }
-
-  // tile times a vector in shared memory -> the entry of the owned row
-  __device__ __forceinline__ double tile_dot(const double* __restrict__ vec) const {
+  // One ADMM iteration: KKT solve = tile times the right-hand side in `vec`, then the
+  // relaxation / projection / dual update of the owned row, then its entry of the next right-hand side into `nxt`.
+  // With yr = y/rho the dependent chain after the solve result t is  zt -> zr -> v -> clip -> rhs:
+  //   v = zr + yr, z+ = clip(v), yr+ = v - z+, next rhs (general row) = z+ - yr+.
+  __device__ __forceinline__ void iterate(const double* __restrict__ vec, double* __restrict__ nxt, double alpha,
+                                          double oma, double sigma) {
     const double2* v2 = reinterpret_cast<const double2*>(vec + c0);
     double s0[TR];
 #pragma unroll
@@ -289,7 +288,30 @@ struct RegSolver {
 #pragma unroll
       for (int r = 0; r < TR; r++) s0[r] = fma(a[r][2 * c + 1], v.y, fma(a[r][2 * c], v.x, s0[r]));
     }
-    return group_reduce<false>(s0, q);
+    // everything that does not depend on the solve result is fetched / computed before the shuffle reduction
+    const double rinv = sc(5, row), lo = sc(1, row), up = sc(2, row), cb = sc(3, row), qs = sc(0, row),
+                 cbrho = sc(12, row);
+    const double w = z - yr, oz = oma * z, ox = oma * x;
+    asm volatile("" ::"d"(rinv), "d"(lo), "d"(up), "d"(cb), "d"(qs), "d"(cbrho), "d"(w), "d"(oz), "d"(ox));
+    const double t = -group_reduce<false>(s0, q);
+    double rhs = 0.0, rw = 0.0;
+    if (isx) {
+      x = fma(alpha, t, ox);
+      rhs = fma(sigma, x, -qs);
+    }
+    if (hasc) {
+      const double zt = isg ? fma(t, rinv, w) : cb * t;
+      const double zr = fma(alpha, zt, oz);
+      const double v = zr + yr;
+      double zn = v < lo ? lo : v;
+      zn = zn > up ? up : zn;
+      yr = v - zn;
+      z = zn;
+      rw = zn - yr;
+    }
+    if (isg) rhs = rw;
+    else if (hasbox) rhs = fma(cbrho, rw, rhs);
+    if (h == 0) nxt[row] = rhs;
   }
 
   // product of the owned row of the scaled, unswept matrix with a vector in shared memory
@@ -351,7 +373,7 @@ struct RegSolver {
     }
     x = 0.0;
     z = 0.0;
-    y = 0.0;
+    yr = 0.0;
     double qs = 0.0, cb = 0.0, l = 0.0, u = 0.0;
     double D = 1.0, E = 1.0;  // accumulated Ruiz scalings of the owned row (E: its constraint row)
     if (isx) qs = pb_.qv[xi];
@@ -375,7 +397,10 @@ struct RegSolver {
       for (int r = 0; r < TR; r++) {
         double v = 0.0;
 #pragma unroll
-        for (int c = 0; c < TC; c++) v = fmax(v, fabs(a[r][c]));
+        for (int c = 0; c < TC; c++) {
+          const double t = fabs(a[r][c]);
+          v = t > v ? t : v;
+        }
         nr4[r] = v;
       }
       double nr = group_reduce<true>(nr4, q);
@@ -413,7 +438,10 @@ struct RegSolver {
         const bool xr = 4 * g + r >= mg;
 #pragma unroll
         for (int c = 0; c < TC; c++)
-          if (xr && c0 + c >= mg) v = fmax(v, fabs(a[r][c]));
+          if (xr && c0 + c >= mg) {
+            const double t = fabs(a[r][c]);
+            v = t > v ? t : v;
+          }
         pn4[r] = v;
       }
       const double pn = group_reduce<true>(pn4, q);
@@ -485,8 +513,7 @@ struct RegSolver {
         double* un = uv + (iter & 1) * US;
 #pragma unroll 1
         for (int k = next_special - iter - 1; k > 0; k--) {
-          update_row(-tile_dot(ub_), alpha, oma);
-          if (h == 0) un[row] = rhs_entry(sigma);
+          iterate(ub_, un, alpha, oma, sigma);
           __syncthreads();
           const double* tmp = ub_;
           ub_ = un;
@@ -498,11 +525,11 @@ struct RegSolver {
       const bool check = iter == next_chk, adapt = iter == next_ada;
       if (h == 0) {
         sc(9, row) = x;
-        sc(10, row) = y;
+        sc(10, row) = sc(4, row) * yr;
       }
-      update_row(-tile_dot(uv + (iter & 1) * US), alpha, oma);
+      iterate(uv + (iter & 1) * US, uv + ((iter + 1) & 1) * US, alpha, oma, sigma);
+      const double y = sc(4, row) * yr;
       if (h == 0) {
-        uv[((iter + 1) & 1) * US + row] = rhs_entry(sigma);
         cv[row] = isx ? x : 0.0;
         cv[NP + row] = isg ? y : 0.0;
       }
@@ -631,7 +658,10 @@ struct RegSolver {
         rho_new = fmin(fmax(rho_new, QPC_RHO_MIN), QPC_RHO_MAX);
         if (rho_new > rho0 * st.adaptive_rho_tolerance || rho_new < rho0 / st.adaptive_rho_tolerance) {
           rho0 = rho_new;
+          __syncwarp();
           if (h == 0) set_rho(rho0);
+          __syncwarp();
+          yr = y * sc(5, row);  // y is unchanged by a rho update; yr = y / rho follows the new rho
           refactor = true;
         }
       }
@@ -654,6 +684,7 @@ struct RegSolver {
       const double cinv = CD[1];
       if (isx) pb_.x[xi] = sc(6, row) * x;
       if (pb_.y) {
+        const double y = sc(4, row) * yr;
         if (isg) pb_.y[row] = cinv * sc(6, row) * y;
         if (hasbox) pb_.y[mg + xi - (n - nbx)] = cinv * sc(7, row) * y;
       }

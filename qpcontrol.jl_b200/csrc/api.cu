@@ -97,12 +97,12 @@ template <int C>
 struct RegTraits {
   static constexpr int MAXT = 16 * C;
   // registers per thread chosen so that the intended number of CTAs per SM fits the 64K-register file with the
-  // per-warp allocation granularity: 128 -> 3 CTAs of 160 threads (TC = 10), 4 of 128 (TC = 8); larger tiles run
-  // 2 or 1 CTA per SM
+  // 16K registers of each SM sub-partition: 128 -> 3 CTAs of 160 threads (TC = 10), 4 of 128 (TC = 8); larger tiles
+  // run 1 CTA per SM
 #ifndef QPC_REGS10
 #define QPC_REGS10 128
 #endif
-  static constexpr int MAXREG = C <= 8 ? 128 : (C <= 10 ? QPC_REGS10 : (C <= 12 ? 168 : (C <= 14 ? 255 : (C <= 16 ? 240 : 200))));
+  static constexpr int MAXREG = C <= 8 ? 128 : (C <= 10 ? QPC_REGS10 : (C <= 14 ? 255 : 240));
 };
 template <int C>
 __global__ void __launch_bounds__(RegTraits<C>::MAXT) __maxnreg__(RegTraits<C>::MAXREG)
@@ -218,7 +218,8 @@ static int launch_grid(long long B) { return (int)(B < (1ll << 30) ? B : (1ll <<
 
 // ---- ADMM dispatch: register-resident kernel when the KKT matrix fits the register file, shared-memory kernel otherwise
 static int reg_columns(int NK) {
-  static const int sizes[] = {2, 4, 6, 8, 10, 12, 14, 16, 18};
+  // TC = 18 (9 warps) cannot launch: registers are per SM sub-partition (16K each), 3 warps x 32 x 144+ > 16384
+  static const int sizes[] = {2, 4, 6, 8, 10, 12, 14, 16};
   const char* e = getenv("QPC_ADMM_SMEM");
   if (e && e[0] == '1') return 0;
   for (int c : sizes)
@@ -264,7 +265,6 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
     case 12: return launch_reg<12>(st, qb, n, mg, nbx, B, stream);
     case 14: return launch_reg<14>(st, qb, n, mg, nbx, B, stream);
     case 16: return launch_reg<16>(st, qb, n, mg, nbx, B, stream);
-    case 18: return launch_reg<18>(st, qb, n, mg, nbx, B, stream);
 #endif
     case 10: return launch_reg<10>(st, qb, n, mg, nbx, B, stream);
     default: break;
@@ -666,7 +666,7 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
         (e = up(ub, B * nbox, qb.ub)) || (e = up(nullptr, B * n, qb.x)) || (e = up(nullptr, B * m, qb.y)) ||
         (e = up(nullptr, B * 2, qb.res)) || (e = cudaMalloc((void**)&dstat, sizeof(int) * B)) ||
         (e = cudaMalloc((void**)&diter, sizeof(int) * B))) {
-      rc = qpc_fail(QPC_ERR_CUDA, cudaGetErrorString(e));
+      rc = qpc_fail(QPC_ERR_CUDA, std::string(cudaGetErrorString(e)) + g_launch_note);
       break;
     }
     qb.status = dstat;
@@ -677,7 +677,7 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
         (e = cudaMemcpy(status, dstat, sizeof(int) * B, cudaMemcpyDeviceToHost)) ||
         (iters && (e = cudaMemcpy(iters, diter, sizeof(int) * B, cudaMemcpyDeviceToHost))) ||
         (residuals && (e = cudaMemcpy(residuals, qb.res, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost)))) {
-      rc = qpc_fail(QPC_ERR_CUDA, cudaGetErrorString(e));
+      rc = qpc_fail(QPC_ERR_CUDA, std::string(cudaGetErrorString(e)) + g_launch_note);
       break;
     }
   } while (0);
