@@ -29,15 +29,15 @@
 
 namespace qpc {
 
-constexpr int REG_MAXW = 12;  // warps per CTA supported by the reduction scratch
-constexpr int REG_NB = 8;     // column blocks (lanes per row group)
+constexpr int REG_MAXW = 16;  // warps per CTA supported by the reduction scratch
 constexpr int REG_TR = 4;     // rows per thread
 
-QPC_HD int admm_reg_positions(int TC) { return REG_NB * TC; }
-QPC_HD int admm_reg_threads(int TC) { return 2 * REG_NB * TC; }  // (NP / 4 row groups) x 8 column blocks
-QPC_HD int admm_reg_smem_doubles(int TC) {
-  const int NP = REG_NB * TC;
-  return REG_TR * TC * admm_reg_threads(TC) + 2 * (2 * NP + 2) + 2 * NP + 3 * REG_MAXW * 16 + 13 * NP + 16;
+// NB = column blocks = lanes per row group (8 or 16); TC = tile columns per thread; NP = NB TC positions
+QPC_HD int admm_reg_positions(int TC, int NB) { return NB * TC; }
+QPC_HD int admm_reg_threads(int TC, int NB) { return (NB * TC / REG_TR) * NB; }  // (NP / 4 row groups) x NB blocks
+QPC_HD int admm_reg_smem_doubles(int TC, int NB) {
+  const int NP = NB * TC;
+  return REG_TR * TC * admm_reg_threads(TC, NB) + 2 * (2 * NP + 2) + 2 * NP + 3 * REG_MAXW * 16 + 13 * NP + 16;
 }
 
 #if defined(__CUDACC__)
@@ -90,26 +90,58 @@ __device__ __forceinline__ double red_get(const double* red, int k) {
   return IS_MAX ? warp_max_nonneg(t) : warp_sum(t);
 }
 
-// Transpose-reduction over the 8 lanes (column blocks) of a row group: every lane enters with partial results for
-// its 4 tile rows and leaves with the complete result of row (q >> 1) & 3, the row it owns.  4 exchanges.
-template <bool IS_MAX>
+// Transpose-reduction over the NB lanes (column blocks) of a row group: every lane enters with partial results for
+// its 4 tile rows and leaves with the complete result of the row it owns, row (q / (NB/4)) & 3.  The first two
+// exchanges halve the number of values carried (keep one half, send the other), the rest are plain all-reduces.
+template <bool IS_MAX, int NB>
 __device__ __forceinline__ double group_reduce(const double (&s)[REG_TR], int q) {
   auto comb = [](double a, double b) { return IS_MAX ? fmax(a, b) : a + b; };
-  const bool hi4 = q & 4, hi2 = q & 2;
-  const double k0 = hi4 ? s[2] : s[0], k1 = hi4 ? s[3] : s[1];
-  const double o0 = hi4 ? s[0] : s[2], o1 = hi4 ? s[1] : s[3];
-  const double r0 = comb(k0, __shfl_xor_sync(0xffffffffu, o0, 4));
-  const double r1 = comb(k1, __shfl_xor_sync(0xffffffffu, o1, 4));
-  const double k = hi2 ? r1 : r0, o = hi2 ? r0 : r1;
-  double v = comb(k, __shfl_xor_sync(0xffffffffu, o, 2));
-  v = comb(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  const bool hiA = q & (NB / 2), hiB = q & (NB / 4);
+  const double k0 = hiA ? s[2] : s[0], k1 = hiA ? s[3] : s[1];
+  const double o0 = hiA ? s[0] : s[2], o1 = hiA ? s[1] : s[3];
+  const double r0 = comb(k0, __shfl_xor_sync(0xffffffffu, o0, NB / 2));
+  const double r1 = comb(k1, __shfl_xor_sync(0xffffffffu, o1, NB / 2));
+  const double k = hiB ? r1 : r0, o = hiB ? r0 : r1;
+  double v = comb(k, __shfl_xor_sync(0xffffffffu, o, NB / 4));
+#pragma unroll
+  for (int d = NB / 8; d > 0; d >>= 1) v = comb(v, __shfl_xor_sync(0xffffffffu, v, d));
   return v;
 }
 
+// TC doubles at `p` (8-byte aligned; 16-byte aligned when TC is even) -> registers
 template <int TC>
+__device__ __forceinline__ void load_vec(const double* __restrict__ p, double (&v)[TC]) {
+  if constexpr (TC % 2 == 0) {
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int c = 0; c < TC / 2; c++) {
+      const double2 t = p2[c];
+      v[2 * c] = t.x;
+      v[2 * c + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < TC; c++) v[c] = p[c];
+  }
+}
+template <int TC>
+__device__ __forceinline__ void store_vec(double* __restrict__ p, const double (&v)[TC]) {
+  if constexpr (TC % 2 == 0) {
+    double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll
+    for (int c = 0; c < TC / 2; c++) p2[c] = make_double2(v[2 * c], v[2 * c + 1]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < TC; c++) p[c] = v[c];
+  }
+}
+
+template <int TC, int NB>
 struct RegSolver {
-  static constexpr int NP = REG_NB * TC;      // row / column positions: general rows (mg), x rows (n), padding
-  static constexpr int NT = 2 * REG_NB * TC;  // threads
+  static_assert(NB == 8 || NB == 16, "lanes per row group");
+  static constexpr int NP = NB * TC;               // row / column positions: general rows (mg), x rows (n), padding
+  static constexpr int NT = (NP / REG_TR) * NB;    // threads
+  static constexpr int LPR = NB / REG_TR;          // lanes that own the same row (they hold identical row state)
   static constexpr int TR = REG_TR;
   static constexpr int US = NP + 2;           // stride of the double-buffered iteration vectors
   static constexpr int PS = 2 * NP + 2;       // stride of the double-buffered published pivot rows (same storage)
@@ -174,9 +206,7 @@ struct RegSolver {
     // symmetry, the multiplier of row j), [2 NP] 1 / pivot.
     double* pb = uv;
     auto publish = [&](double* pw, const double (&rowv)[TC], int sm1, bool pivot_lane) {
-      double2* pw2 = reinterpret_cast<double2*>(pw + c0);
-#pragma unroll
-      for (int c = 0; c < TC / 2; c++) pw2[c] = make_double2(rowv[2 * c], rowv[2 * c + 1]);
+      store_vec<TC>(pw + c0, rowv);
 #pragma unroll
       for (int c = 0; c < TC; c++) {
         int idx = c + sm1;
@@ -215,31 +245,24 @@ struct RegSolver {
           f[3] = fb.y * dinv;
         }
         const bool inb = q == b;
-        const double2* p2 = reinterpret_cast<const double2*>(pr + c0);
         double t0[TR];
 #pragma unroll
         for (int r = 0; r < TR; r++) t0[r] = a[r][0];
-        double p0 = 0.0;
-        // a[r][c-1] <- a[r][c] - f[r] p[c]  (the pivot row itself: a[r][c] / pivot), two columns per 16-byte load
+        double p[TC];
+        load_vec<TC>(pr + c0, p);
+        // a[r][c-1] <- a[r][c] - f[r] p[c]  (the pivot row itself: a[r][c] / pivot)
 #pragma unroll
-        for (int c2 = 0; c2 < TC / 2; c2++) {
-          const double2 v = p2[c2];
-          if (c2 == 0) p0 = v.x;
+        for (int c = 1; c < TC; c++) {
 #pragma unroll
           for (int r = 0; r < TR; r++) {
-            if (r == rr && own) {
-              if (c2 > 0) a[r][2 * c2 - 1] = a[r][2 * c2] * dinv;
-              a[r][2 * c2] = a[r][2 * c2 + 1] * dinv;
-            } else {
-              if (c2 > 0) a[r][2 * c2 - 1] = fma(-f[r], v.x, a[r][2 * c2]);
-              a[r][2 * c2] = fma(-f[r], v.y, a[r][2 * c2 + 1]);
-            }
+            if (r == rr && own) a[r][c - 1] = a[r][c] * dinv;
+            else a[r][c - 1] = fma(-f[r], p[c], a[r][c]);
           }
         }
 #pragma unroll
         for (int r = 0; r < TR; r++) {
           if (r == rr && own) a[r][TC - 1] = inb ? -dinv : t0[r] * dinv;
-          else a[r][TC - 1] = inb ? f[r] : fma(-f[r], p0, t0[r]);
+          else a[r][TC - 1] = inb ? f[r] : fma(-f[r], p[0], t0[r]);
         }
         // publish the next pivot row (position s + 1: row group (s + 1) / 4, tile row (rr + 1) % 4)
         const int s1 = s + 1;
@@ -278,22 +301,22 @@ struct RegSolver {
   //   v = zr + yr, z+ = clip(v), yr+ = v - z+, next rhs (general row) = z+ - yr+.
   __device__ __forceinline__ void iterate(const double* __restrict__ vec, double* __restrict__ nxt, double alpha,
                                           double oma, double sigma) {
-    const double2* v2 = reinterpret_cast<const double2*>(vec + c0);
+    double u[TC];
+    load_vec<TC>(vec + c0, u);
     double s0[TR];
 #pragma unroll
     for (int r = 0; r < TR; r++) s0[r] = 0.0;
 #pragma unroll
-    for (int c = 0; c < TC / 2; c++) {
-      const double2 v = v2[c];
+    for (int c = 0; c < TC; c++) {
 #pragma unroll
-      for (int r = 0; r < TR; r++) s0[r] = fma(a[r][2 * c + 1], v.y, fma(a[r][2 * c], v.x, s0[r]));
+      for (int r = 0; r < TR; r++) s0[r] = fma(a[r][c], u[c], s0[r]);
     }
     // everything that does not depend on the solve result is fetched / computed before the shuffle reduction
     const double rinv = sc(5, row), lo = sc(1, row), up = sc(2, row), cb = sc(3, row), qs = sc(0, row),
                  cbrho = sc(12, row);
     const double w = z - yr, oz = oma * z, ox = oma * x;
     asm volatile("" ::"d"(rinv), "d"(lo), "d"(up), "d"(cb), "d"(qs), "d"(cbrho), "d"(w), "d"(oz), "d"(ox));
-    const double t = -group_reduce<false>(s0, q);
+    const double t = -group_reduce<false, NB>(s0, q);
     double rhs = 0.0, rw = 0.0;
     if (isx) {
       x = fma(alpha, t, ox);
@@ -325,7 +348,7 @@ struct RegSolver {
 #pragma unroll
       for (int r = 0; r < TR; r++) s0[r] = fma(K0[(r * TC + c) * NT + tid], e, s0[r]);
     }
-    return group_reduce<false>(s0, q);
+    return group_reduce<false, NB>(s0, q);
   }
   // x-rows get (P vx, G' vy), general rows get (G vx, 0)
   __device__ __forceinline__ void k0_products(const double* vx, const double* vy, double& px, double& py) const {
@@ -335,11 +358,11 @@ struct RegSolver {
 
   __device__ void solve(const Settings& st, const AdmmProblem& pb_, double* smem) {
     tid = threadIdx.x;
-    q = tid & 7;
-    g = tid >> 3;
+    q = tid % NB;
+    g = tid / NB;
     c0 = q * TC;
-    row = 4 * g + ((q >> 1) & 3);
-    h = q & 1;
+    row = 4 * g + ((q / LPR) & 3);
+    h = q % LPR;  // lane 0 of the LPR lanes that own a row does the writing
     NK = n + mg;
     isg = row < mg;
     isx = row >= mg && row < NK;
@@ -359,7 +382,7 @@ struct RegSolver {
     __syncthreads();
     auto k0_index = [&](int i, int j) {  // element (row position i, column position j)
       const int qq = j / TC;
-      return ((i & 3) * TC + (j - qq * TC)) * NT + (i >> 2) * 8 + qq;
+      return ((i & 3) * TC + (j - qq * TC)) * NT + (i >> 2) * NB + qq;
     };
     for (int k = tid; k < n * n; k += NT) {
       const int i = k / n, j = k - i * n;
@@ -403,7 +426,7 @@ struct RegSolver {
         }
         nr4[r] = v;
       }
-      double nr = group_reduce<true>(nr4, q);
+      double nr = group_reduce<true, NB>(nr4, q);
       if (hasbox) nr = fmax(nr, fabs(cb));
       const double sr = row < NK ? 1.0 / sqrt(limit_scaling(nr)) : 1.0;
       const double eb = hasbox ? 1.0 / sqrt(limit_scaling(fabs(cb))) : 1.0;
@@ -444,7 +467,7 @@ struct RegSolver {
           }
         pn4[r] = v;
       }
-      const double pn = group_reduce<true>(pn4, q);
+      const double pn = group_reduce<true, NB>(pn4, q);
       double v2[2];
       v2[0] = isx ? fabs(qs) : 0.0;
       v2[1] = (isx && h == 0) ? pn : 0.0;

@@ -92,20 +92,17 @@ qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B, 
   }
 }
 
-// register-resident variant (admm_reg.cuh): TC = tile columns per thread, 8 TC >= n + mg
-template <int C>
+// register-resident variant (admm_reg.cuh): 4 x TC register tiles, NB column blocks, NB TC >= n + mg positions
+template <int TC, int NB>
 struct RegTraits {
-  static constexpr int MAXT = 16 * C;
-  // registers per thread chosen so that the intended number of CTAs per SM fits the 64K-register file with the
-  // 16K registers of each SM sub-partition: 128 -> 3 CTAs of 160 threads (TC = 10), 4 of 128 (TC = 8); larger tiles
-  // run 1 CTA per SM
-#ifndef QPC_REGS10
-#define QPC_REGS10 128
-#endif
-  static constexpr int MAXREG = C <= 8 ? 128 : (C <= 10 ? QPC_REGS10 : (C <= 14 ? 255 : 240));
+  static constexpr int MAXT = (NB * TC / 4) * NB;
+  // Registers per thread, chosen against the 16K registers of each SM sub-partition (warps of all resident CTAs are
+  // spread over the four of them): NB = 16, TC = 5 -> 320 threads, 2 CTAs/SM = 5 warps per sub-partition -> 96;
+  // NB = 8: 128 -> 3 CTAs of 160 threads (TC = 10), 4 of 128 (TC = 8); larger tiles run 1 CTA per SM.
+  static constexpr int MAXREG = NB == 16 ? 96 : (TC <= 10 ? 128 : (TC <= 14 ? 255 : 240));
 };
-template <int C>
-__global__ void __launch_bounds__(RegTraits<C>::MAXT) __maxnreg__(RegTraits<C>::MAXREG)
+template <int TC, int NB>
+__global__ void __launch_bounds__((RegTraits<TC, NB>::MAXT)) __maxnreg__((RegTraits<TC, NB>::MAXREG))
 qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B) {
   extern __shared__ double smem[];
   for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
@@ -123,7 +120,7 @@ qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long
     pb.iters = qb.iters ? qb.iters + inst : nullptr;
     pb.res = qb.res ? qb.res + 2 * inst : nullptr;
     pb.nfac = qb.nfac ? qb.nfac + inst : nullptr;
-    RegSolver<C> s;
+    RegSolver<TC, NB> s;
     s.n = n;
     s.mg = mg;
     s.nbx = nbx;
@@ -217,56 +214,63 @@ static int upload_program(qpc_controller* c) {
 static int launch_grid(long long B) { return (int)(B < (1ll << 30) ? B : (1ll << 30)); }
 
 // ---- ADMM dispatch: register-resident kernel when the KKT matrix fits the register file, shared-memory kernel otherwise
-static int reg_columns(int NK) {
-  // TC = 18 (9 warps) cannot launch: registers are per SM sub-partition (16K each), 3 warps x 32 x 144+ > 16384
-  static const int sizes[] = {2, 4, 6, 8, 10, 12, 14, 16};
+// returns a code TC * 100 + NB, or 0 for the shared-memory kernel
+static int reg_tile(int NK) {
   const char* e = getenv("QPC_ADMM_SMEM");
   if (e && e[0] == '1') return 0;
+  // QPC_ADMM_TILE=5x16: the 16-lane tiling (320 threads, 2 CTAs/SM, no spills) for 64 < NK <= 80.  Measured on the Atlas
+  // workload it is 20 % slower than 10x8 (3 CTAs/SM): twice the warps pay the reduction and the row update.
+  const char* t = getenv("QPC_ADMM_TILE");
+  if (t && t[0] == '5' && NK > 64 && NK <= 80) return 5 * 100 + 16;
+  // TC = 18 (9 warps) cannot launch: 3 warps x 32 x 144+ registers exceed a 16K sub-partition
+  static const int sizes[] = {2, 4, 6, 8, 10, 12, 14, 16};
   for (int c : sizes)
-    if (admm_reg_positions(c) >= NK) return c;
+    if (admm_reg_positions(c, 8) >= NK) return c * 100 + 8;
   return 0;
 }
-template <int C>
+template <int TC, int NB>
 static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long B,
                               cudaStream_t stream) {
-  const int NT = admm_reg_threads(C);
-  const int bytes = admm_reg_smem_doubles(C) * 8;
+  const int NT = admm_reg_threads(TC, NB);
+  const int bytes = admm_reg_smem_doubles(TC, NB) * 8;
   static int configured[64] = {0};  // per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && configured[dev] < bytes) {
-    cudaError_t e = cudaFuncSetAttribute(qpc_admm_reg_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(qpc_admm_reg_kernel<TC, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(qpc_admm_reg_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(qpc_admm_reg_kernel<TC, NB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = bytes;
   }
-  qpc_admm_reg_kernel<C><<<launch_grid(B), NT, bytes, stream>>>(st, qb, n, mg, nbx, B);
+  qpc_admm_reg_kernel<TC, NB><<<launch_grid(B), NT, bytes, stream>>>(st, qb, n, mg, nbx, B);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, qpc_admm_reg_kernel<C>) == cudaSuccess)
-      g_launch_note = " [admm_reg TC=" + std::to_string(C) + " threads=" + std::to_string(NT) + " regs=" +
-                      std::to_string(fa.numRegs) + " dyn_smem=" + std::to_string(bytes) + " static_smem=" +
-                      std::to_string(fa.sharedSizeBytes) + " local=" + std::to_string(fa.localSizeBytes) + "]";
+    if (cudaFuncGetAttributes(&fa, qpc_admm_reg_kernel<TC, NB>) == cudaSuccess)
+      g_launch_note = " [admm_reg TC=" + std::to_string(TC) + " NB=" + std::to_string(NB) + " threads=" +
+                      std::to_string(NT) + " regs=" + std::to_string(fa.numRegs) + " dyn_smem=" + std::to_string(bytes) +
+                      " static_smem=" + std::to_string(fa.sharedSizeBytes) + " local=" +
+                      std::to_string(fa.localSizeBytes) + "]";
   }
   return le;
 }
 // returns cudaSuccess or the launch error; `smem_configured` = the v1 kernel's attribute was already set for this size
 static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long B,
                                cudaStream_t stream) {
-  switch (reg_columns(n + mg)) {
-#ifndef QPC_ONLY_TC10  /* development builds (register-liveness dumps) instantiate the Atlas tile only */
-    case 2: return launch_reg<2>(st, qb, n, mg, nbx, B, stream);
-    case 4: return launch_reg<4>(st, qb, n, mg, nbx, B, stream);
-    case 6: return launch_reg<6>(st, qb, n, mg, nbx, B, stream);
-    case 8: return launch_reg<8>(st, qb, n, mg, nbx, B, stream);
-    case 12: return launch_reg<12>(st, qb, n, mg, nbx, B, stream);
-    case 14: return launch_reg<14>(st, qb, n, mg, nbx, B, stream);
-    case 16: return launch_reg<16>(st, qb, n, mg, nbx, B, stream);
+  switch (reg_tile(n + mg)) {
+    case 516: return launch_reg<5, 16>(st, qb, n, mg, nbx, B, stream);
+    case 1008: return launch_reg<10, 8>(st, qb, n, mg, nbx, B, stream);
+#ifndef QPC_ONLY_ATLAS  /* development builds (register-liveness dumps) instantiate the Atlas tiles only */
+    case 208: return launch_reg<2, 8>(st, qb, n, mg, nbx, B, stream);
+    case 408: return launch_reg<4, 8>(st, qb, n, mg, nbx, B, stream);
+    case 608: return launch_reg<6, 8>(st, qb, n, mg, nbx, B, stream);
+    case 808: return launch_reg<8, 8>(st, qb, n, mg, nbx, B, stream);
+    case 1208: return launch_reg<12, 8>(st, qb, n, mg, nbx, B, stream);
+    case 1408: return launch_reg<14, 8>(st, qb, n, mg, nbx, B, stream);
+    case 1608: return launch_reg<16, 8>(st, qb, n, mg, nbx, B, stream);
 #endif
-    case 10: return launch_reg<10>(st, qb, n, mg, nbx, B, stream);
     default: break;
   }
   const int asmem = admm_smem_doubles(n, mg, nbx) * 8;
