@@ -29,6 +29,11 @@ struct Backend {
   bool profiling = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int* d_nfac = nullptr;  // [capB] factorisations per instance
+  // chunked tick: sub-batches go to side streams so that one chunk's assembly / inverse dynamics and the tail of its
+  // ADMM kernel overlap the next chunk's ADMM kernel
+  static constexpr int NSIDE = 4;
+  cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 #include "admm.cuh"
@@ -52,9 +57,9 @@ constexpr int ADMM_THREADS = 128;
 constexpr int ID_THREADS = 64;
 
 __global__ void __launch_bounds__(ASM_THREADS)
-qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb, long long B) {
+qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb, long long base, long long B) {
   extern __shared__ double smem[];
-  for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
+  for (long long inst = base + blockIdx.x; inst < B; inst += gridDim.x) {
     KinSmem s = kin_layout(smem, pg->nb, pg->nq, pg->nv, pg->ndes, pg->ncontacts, pg->N);
     kin_load(pg, io, inst, s);
     kin_forward(pg, s);
@@ -70,10 +75,10 @@ qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb,
 }
 
 __global__ void __launch_bounds__(ADMM_THREADS)
-qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B, double* gscratch) {
+qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long base, long long B, double* gscratch) {
   extern __shared__ double smem[];
   double* gmat = gscratch ? gscratch + (size_t)blockIdx.x * admm_matrix_doubles(n, mg) : nullptr;
-  for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
+  for (long long inst = base + blockIdx.x; inst < B; inst += gridDim.x) {
     AdmmProblem pb;
     pb.P = qb.P + inst * n * n;
     pb.qv = qb.qv + inst * n;
@@ -103,9 +108,9 @@ struct RegTraits {
 };
 template <int TC, int NB>
 __global__ void __launch_bounds__((RegTraits<TC, NB>::MAXT)) __maxnreg__((RegTraits<TC, NB>::MAXREG))
-qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long B) {
+qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long base, long long B) {
   extern __shared__ double smem[];
-  for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
+  for (long long inst = base + blockIdx.x; inst < B; inst += gridDim.x) {
     AdmmProblem pb;
     pb.P = qb.P + inst * n * n;
     pb.qv = qb.qv + inst * n;
@@ -129,8 +134,8 @@ qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long
 }
 
 // status for programs whose QP has no free variable (everything fixed by hard joint tasks)
-__global__ void qpc_trivial_status_kernel(int* status, int* iters, double* res, long long B) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+__global__ void qpc_trivial_status_kernel(int* status, int* iters, double* res, long long base, long long B) {
+  long long i = base + blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < B) {
     status[i] = 1;
     if (iters) iters[i] = 0;
@@ -140,9 +145,9 @@ __global__ void qpc_trivial_status_kernel(int* status, int* iters, double* res, 
 
 __global__ void __launch_bounds__(ID_THREADS)
 qpc_inverse_dynamics_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb, double* tau, double* vdot,
-                            double* wrench, long long B) {
+                            double* wrench, long long base, long long B) {
   extern __shared__ double smem[];
-  for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
+  for (long long inst = base + blockIdx.x; inst < B; inst += gridDim.x) {
     KinSmem s = kin_layout(smem, pg->nb, pg->nq, pg->nv, pg->ndes, pg->ncontacts, pg->N);
     kin_load(pg, io, inst, s);
     for (int i = threadIdx.x; i < pg->ndes; i += blockDim.x) s.des[i] = qb.des[inst * pg->ndes + i];
@@ -229,8 +234,8 @@ static int reg_tile(int NK) {
   return 0;
 }
 template <int TC, int NB>
-static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long B,
-                              cudaStream_t stream) {
+static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long base,
+                              long long B, cudaStream_t stream) {
   const int NT = admm_reg_threads(TC, NB);
   const int bytes = admm_reg_smem_doubles(TC, NB) * 8;
   static int configured[64] = {0};  // per device
@@ -244,7 +249,7 @@ static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, in
     if (e != cudaSuccess) return e;
     configured[dev] = bytes;
   }
-  qpc_admm_reg_kernel<TC, NB><<<launch_grid(B), NT, bytes, stream>>>(st, qb, n, mg, nbx, B);
+  qpc_admm_reg_kernel<TC, NB><<<launch_grid(B - base), NT, bytes, stream>>>(st, qb, n, mg, nbx, base, B);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     cudaFuncAttributes fa;
@@ -257,25 +262,26 @@ static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, in
   return le;
 }
 // returns cudaSuccess or the launch error; `smem_configured` = the v1 kernel's attribute was already set for this size
-static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long B,
-                               cudaStream_t stream) {
+// instances [base, B)
+static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long base,
+                               long long B, cudaStream_t stream) {
   switch (reg_tile(n + mg)) {
-    case 516: return launch_reg<5, 16>(st, qb, n, mg, nbx, B, stream);
-    case 1008: return launch_reg<10, 8>(st, qb, n, mg, nbx, B, stream);
+    case 516: return launch_reg<5, 16>(st, qb, n, mg, nbx, base, B, stream);
+    case 1008: return launch_reg<10, 8>(st, qb, n, mg, nbx, base, B, stream);
 #ifndef QPC_ONLY_ATLAS  /* development builds (register-liveness dumps) instantiate the Atlas tiles only */
-    case 208: return launch_reg<2, 8>(st, qb, n, mg, nbx, B, stream);
-    case 408: return launch_reg<4, 8>(st, qb, n, mg, nbx, B, stream);
-    case 608: return launch_reg<6, 8>(st, qb, n, mg, nbx, B, stream);
-    case 808: return launch_reg<8, 8>(st, qb, n, mg, nbx, B, stream);
-    case 1208: return launch_reg<12, 8>(st, qb, n, mg, nbx, B, stream);
-    case 1408: return launch_reg<14, 8>(st, qb, n, mg, nbx, B, stream);
-    case 1608: return launch_reg<16, 8>(st, qb, n, mg, nbx, B, stream);
+    case 208: return launch_reg<2, 8>(st, qb, n, mg, nbx, base, B, stream);
+    case 408: return launch_reg<4, 8>(st, qb, n, mg, nbx, base, B, stream);
+    case 608: return launch_reg<6, 8>(st, qb, n, mg, nbx, base, B, stream);
+    case 808: return launch_reg<8, 8>(st, qb, n, mg, nbx, base, B, stream);
+    case 1208: return launch_reg<12, 8>(st, qb, n, mg, nbx, base, B, stream);
+    case 1408: return launch_reg<14, 8>(st, qb, n, mg, nbx, base, B, stream);
+    case 1608: return launch_reg<16, 8>(st, qb, n, mg, nbx, base, B, stream);
 #endif
     default: break;
   }
   const int asmem = admm_smem_doubles(n, mg, nbx) * 8;
   if (asmem <= 227 * 1024) {
-    qpc_admm_kernel<<<launch_grid(B), ADMM_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, B, nullptr);
+    qpc_admm_kernel<<<launch_grid(B - base), ADMM_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, base, B, nullptr);
     return cudaGetLastError();
   }
   // QPs that fit neither the register file nor shared memory: matrices in a per-CTA global scratch (L2 resident for
@@ -285,13 +291,13 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long grid = B < 2ll * sms ? B : 2ll * sms;
+  const long long grid = B - base < 2ll * sms ? B - base : 2ll * sms;
   double* scratch = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)grid * admm_matrix_doubles(n, mg), stream);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vsmem);
   if (e == cudaSuccess) {
-    qpc_admm_kernel<<<(int)grid, ADMM_THREADS, vsmem, stream>>>(st, qb, n, mg, nbx, B, scratch);
+    qpc_admm_kernel<<<(int)grid, ADMM_THREADS, vsmem, stream>>>(st, qb, n, mg, nbx, base, B, scratch);
     e = cudaGetLastError();
   }
   cudaFreeAsync(scratch, stream);
@@ -327,9 +333,18 @@ static QpBuffers qp_view(const DeviceBuffers& b) {
   return q;
 }
 
+// host buffers of a QPC_HOST_PTRS call: copied chunk by chunk on the chunk's own stream so that PCIe transfers overlap
+// the other chunks' kernels
+struct HostXfer {
+  const qpc_batch_in* in;
+  const qpc_batch_out* out;
+  long long dstride, cstride;  // 0 = one broadcast row (copied once, before the fork)
+};
+
 // the tick on device pointers; asynchronous on `stream`
 static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* tau, double* vdot, double* wrench,
-                    int* status, int* iters, double* res, int* nfac, cudaStream_t stream) {
+                    int* status, int* iters, double* res, int* nfac, cudaStream_t stream,
+                    const HostXfer* hx = nullptr) {
   const DevProgram& p = c->prog;
   const DevProgram* dp = (const DevProgram*)c->be.d_prog;
   QpBuffers qb = qp_view(c->be.buf);
@@ -339,18 +354,65 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
   qb.nfac = nfac ? nfac : c->be.d_nfac;
   const bool prof = c->be.profiling;
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
-  const int grid = launch_grid(B);
-  if (prof) cudaEventRecord(c->be.ev[0], stream);
-  qpc_assemble_kernel<<<grid, ASM_THREADS, ksm, stream>>>(dp, io, qb, B);
-  if (prof) cudaEventRecord(c->be.ev[1], stream);
-  if (p.n > 0)
-    CUDA_TRY(launch_admm(p.settings, qb, p.n, p.mg, p.nbx, B, stream));
-  else
-    qpc_trivial_status_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(qb.status, qb.iters, qb.res, B);
-  if (prof) cudaEventRecord(c->be.ev[2], stream);
-  qpc_inverse_dynamics_kernel<<<grid, ID_THREADS, ksm, stream>>>(dp, io, qb, tau, vdot, wrench, B);
-  if (prof) cudaEventRecord(c->be.ev[3], stream);
-  c->be.launches += 3;
+  DeviceBuffers& hb = c->be.buf;
+  auto tick_range = [&](long long lo, long long hi, cudaStream_t s, bool timed) -> int {
+    const int grid = launch_grid(hi - lo);
+    const size_t cnt = (size_t)(hi - lo);
+    if (hx) {  // inputs of this chunk, host -> device staging
+      CUDA_TRY(cudaMemcpyAsync(hb.q + lo * p.nq, hx->in->q + lo * p.nq, sizeof(double) * cnt * p.nq, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(hb.v + lo * p.nv, hx->in->v + lo * p.nv, sizeof(double) * cnt * p.nv, cudaMemcpyHostToDevice, s));
+      if (hx->in->desired && hx->dstride)
+        CUDA_TRY(cudaMemcpyAsync(hb.desired + lo * hx->dstride, hx->in->desired + lo * hx->dstride,
+                                 sizeof(double) * cnt * hx->dstride, cudaMemcpyHostToDevice, s));
+      if (hx->in->contact_weight && hx->cstride) {
+        CUDA_TRY(cudaMemcpyAsync(hb.cw + lo * hx->cstride, hx->in->contact_weight + lo * hx->cstride,
+                                 sizeof(double) * cnt * hx->cstride, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(hb.cm + lo * hx->cstride, hx->in->contact_maxnormalforce + lo * hx->cstride,
+                                 sizeof(double) * cnt * hx->cstride, cudaMemcpyHostToDevice, s));
+      }
+    }
+    if (timed) cudaEventRecord(c->be.ev[0], s);
+    qpc_assemble_kernel<<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
+    if (timed) cudaEventRecord(c->be.ev[1], s);
+    if (p.n > 0)
+      CUDA_TRY(launch_admm(p.settings, qb, p.n, p.mg, p.nbx, lo, hi, s));
+    else
+      qpc_trivial_status_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, s>>>(qb.status, qb.iters, qb.res, lo, hi);
+    if (timed) cudaEventRecord(c->be.ev[2], s);
+    qpc_inverse_dynamics_kernel<<<grid, ID_THREADS, ksm, s>>>(dp, io, qb, tau, vdot, wrench, lo, hi);
+    if (timed) cudaEventRecord(c->be.ev[3], s);
+    c->be.launches += 3;
+    if (hx) {  // results of this chunk, device staging -> host
+      const qpc_batch_out* o = hx->out;
+      const int nc6 = p.ncontacts * 6;
+      if (o->tau) CUDA_TRY(cudaMemcpyAsync(o->tau + lo * p.nv, tau + lo * p.nv, sizeof(double) * cnt * p.nv, cudaMemcpyDeviceToHost, s));
+      if (o->vdot) CUDA_TRY(cudaMemcpyAsync(o->vdot + lo * p.nv, vdot + lo * p.nv, sizeof(double) * cnt * p.nv, cudaMemcpyDeviceToHost, s));
+      if (o->wrench) CUDA_TRY(cudaMemcpyAsync(o->wrench + lo * nc6, wrench + lo * nc6, sizeof(double) * cnt * nc6, cudaMemcpyDeviceToHost, s));
+      if (o->status) CUDA_TRY(cudaMemcpyAsync(o->status + lo, qb.status + lo, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
+      if (o->iters) CUDA_TRY(cudaMemcpyAsync(o->iters + lo, qb.iters + lo, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
+      if (o->residuals) CUDA_TRY(cudaMemcpyAsync(o->residuals + 2 * lo, qb.res + 2 * lo, sizeof(double) * 2 * cnt, cudaMemcpyDeviceToHost, s));
+      if (o->factorizations) CUDA_TRY(cudaMemcpyAsync(o->factorizations + lo, qb.nfac + lo, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s));
+    }
+    return QPC_OK;
+  };
+  // Large batches are cut into NSIDE contiguous chunks on side streams (forked from / joined to the caller's stream):
+  // the GPU then overlaps chunk k's inverse dynamics, chunk k+1's assembly and the tail of chunk k's ADMM kernel with
+  // the bulk of the next ADMM kernel.  Results do not depend on the chunking (instances are independent).
+  const int nchunk = (!prof && B >= 4096 && c->be.side[0]) ? Backend::NSIDE : 1;
+  if (nchunk == 1) {
+    int rc = tick_range(0, B, stream, prof);
+    if (rc) return rc;
+  } else {
+    CUDA_TRY(cudaEventRecord(c->be.fork, stream));
+    for (int k = 0; k < nchunk; k++) {
+      const long long lo = B * k / nchunk, hi = B * (k + 1) / nchunk;
+      CUDA_TRY(cudaStreamWaitEvent(c->be.side[k], c->be.fork, 0));
+      int rc = tick_range(lo, hi, c->be.side[k], false);
+      if (rc) return rc;
+      CUDA_TRY(cudaEventRecord(c->be.join[k], c->be.side[k]));
+      CUDA_TRY(cudaStreamWaitEvent(stream, c->be.join[k], 0));
+    }
+  }
   CUDA_TRY(cudaGetLastError());
   return QPC_OK;
 }
@@ -374,6 +436,11 @@ int qpc_finalize(qpc_controller* c, int32_t device) {
   c->be.device = device;
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->be.stream, cudaStreamNonBlocking));
+  for (int k = 0; k < Backend::NSIDE; k++) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->be.side[k], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->be.join[k], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&c->be.fork, cudaEventDisableTiming));
   int rc = configure_kernels(c->prog);
   if (rc) return rc;
   rc = upload_program(c);
@@ -394,6 +461,11 @@ void qpc_controller_destroy(qpc_controller* c) {
     for (void* p : ptrs)
       if (p) cudaFree(p);
     if (c->be.stream) cudaStreamDestroy(c->be.stream);
+    for (int k = 0; k < Backend::NSIDE; k++) {
+      if (c->be.side[k]) cudaStreamDestroy(c->be.side[k]);
+      if (c->be.join[k]) cudaEventDestroy(c->be.join[k]);
+    }
+    if (c->be.fork) cudaEventDestroy(c->be.fork);
   }
   delete c;
 }
@@ -445,36 +517,27 @@ int qpc_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const 
                     out->factorizations, stream);
   }
   cudaStream_t s = c->be.stream;
-  CUDA_TRY(cudaMemcpyAsync(b.q, in->q, sizeof(double) * B * p.nq, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(b.v, in->v, sizeof(double) * B * p.nv, cudaMemcpyHostToDevice, s));
   io.q = b.q;
   io.v = b.v;
   io.desired = nullptr;
   io.cweight = io.cmaxnf = nullptr;
   if (in->desired) {
-    const long long cnt = dstride ? drows * dstride : p.ndes;
-    CUDA_TRY(cudaMemcpyAsync(b.desired, in->desired, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+    if (!dstride) CUDA_TRY(cudaMemcpyAsync(b.desired, in->desired, sizeof(double) * p.ndes, cudaMemcpyHostToDevice, s));
     io.desired = b.desired;
   }
   if (in->contact_weight) {
-    const long long cnt = cstride ? crows * cstride : p.ncontacts;
-    CUDA_TRY(cudaMemcpyAsync(b.cw, in->contact_weight, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(b.cm, in->contact_maxnormalforce, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+    if (!cstride) {
+      CUDA_TRY(cudaMemcpyAsync(b.cw, in->contact_weight, sizeof(double) * p.ncontacts, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(b.cm, in->contact_maxnormalforce, sizeof(double) * p.ncontacts, cudaMemcpyHostToDevice, s));
+    }
     io.cweight = b.cw;
     io.cmaxnf = b.cm;
   }
-  rc = run_tick(c, B, io, b.tau, b.vdot, b.wrench, b.status, b.iters, b.res, nullptr, s);
+  (void)drows;
+  (void)crows;
+  HostXfer hx{in, out, dstride, cstride};
+  rc = run_tick(c, B, io, b.tau, b.vdot, b.wrench, b.status, b.iters, b.res, nullptr, s, &hx);
   if (rc) return rc;
-  if (out->tau) CUDA_TRY(cudaMemcpyAsync(out->tau, b.tau, sizeof(double) * B * p.nv, cudaMemcpyDeviceToHost, s));
-  if (out->vdot) CUDA_TRY(cudaMemcpyAsync(out->vdot, b.vdot, sizeof(double) * B * p.nv, cudaMemcpyDeviceToHost, s));
-  if (out->wrench)
-    CUDA_TRY(cudaMemcpyAsync(out->wrench, b.wrench, sizeof(double) * B * p.ncontacts * 6, cudaMemcpyDeviceToHost, s));
-  if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, b.status, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-  if (out->iters) CUDA_TRY(cudaMemcpyAsync(out->iters, b.iters, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-  if (out->residuals)
-    CUDA_TRY(cudaMemcpyAsync(out->residuals, b.res, sizeof(double) * 2 * B, cudaMemcpyDeviceToHost, s));
-  if (out->factorizations)
-    CUDA_TRY(cudaMemcpyAsync(out->factorizations, c->be.d_nfac, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return QPC_OK;
 }
@@ -577,7 +640,7 @@ int qpc_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
     qb.lb = lb;
     qb.ub = ub;
     if (desired_out) qb.des = desired_out;
-    qpc_assemble_kernel<<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qb, B);
+    qpc_assemble_kernel<<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qb, 0, B);
     c->be.launches += 1;
     CUDA_TRY(cudaGetLastError());
     return QPC_OK;
@@ -601,7 +664,7 @@ int qpc_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
     io.cweight = b.cw;
     io.cmaxnf = b.cm;
   }
-  qpc_assemble_kernel<<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qp_view(b), B);
+  qpc_assemble_kernel<<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qp_view(b), 0, B);
   c->be.launches += 1;
   CUDA_TRY(cudaGetLastError());
   const long long n = p.n, mg = p.mg, nbx = p.nbx;
@@ -647,7 +710,7 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
     qb.status = status;
     qb.iters = iters;
     qb.res = residuals;
-    CUDA_TRY(launch_admm(s, qb, n, mg, nbox, B, (cudaStream_t)stream_));
+    CUDA_TRY(launch_admm(s, qb, n, mg, nbox, 0, B, (cudaStream_t)stream_));
     return QPC_OK;
   }
   // host pointers: temporary device copies (this entry point serves the synthetic-QP sweep, not the control tick)
@@ -675,7 +738,7 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
     }
     qb.status = dstat;
     qb.iters = diter;
-    if ((e = launch_admm(s, qb, n, mg, nbox, B, nullptr)) || (e = cudaDeviceSynchronize()) ||
+    if ((e = launch_admm(s, qb, n, mg, nbox, 0, B, nullptr)) || (e = cudaDeviceSynchronize()) ||
         (e = cudaMemcpy(x, qb.x, sizeof(double) * B * n, cudaMemcpyDeviceToHost)) ||
         (y && (e = cudaMemcpy(y, qb.y, sizeof(double) * B * m, cudaMemcpyDeviceToHost))) ||
         (e = cudaMemcpy(status, dstat, sizeof(int) * B, cudaMemcpyDeviceToHost)) ||
