@@ -157,6 +157,23 @@ int qpc_stage_times(qpc_controller*, double ms[3]);
 /* fp64 FMA throughput of the device in TFLOP/s (dependent-chain-free DFMA loop), the roofline denominator */
 int qpc_measure_fp64_peak(int32_t device, double* tflops);
 
+/* ---- sequential ticks: warm start and the closed loop ------------------------------------------
+ * The reference solves every tick in the same OSQP workspace, so each solve starts from the previous tick's primal /
+ * dual iterates and the rho it had adapted to (OSQP's implicit warm start behind `solve!`, momentum.jl:58; SURVEY.md
+ * 8(a) a12).  qpc_set_warm_start(ctrl, 1) gives every batch slot that behaviour: the ADMM solve of slot i starts from
+ * the (x, y, rho) slot i ended its previous accepted solve with.  Off by default: every tick is a cold start. */
+int qpc_set_warm_start(qpc_controller*, int32_t on);
+int qpc_reset_warm_start(qpc_controller*); /* forget the stored iterates: the next tick starts cold */
+/* `nsteps` control ticks in closed loop without leaving the device: after every tick the states advance in place by
+ * dt with the commanded accelerations (semi-implicit Euler; the quaternion of a floating joint through the exponential
+ * map) -- the batched counterpart of `simulate(state, T, PeriodicController(tau, dt, controller))` in
+ * notebooks/Standing controller.ipynb:202-214 under the model the controller itself assumes (its contact wrenches are
+ * the ones applied, so forward dynamics returns the commanded vd: test/controller.jl:92-96).  q [B][nq] and v [B][nv]
+ * are read and overwritten (host or device pointers per flags); `in` supplies desired / contact arrays as in
+ * qpc_solve_batch (its q and v are ignored; may be NULL); `out` receives the last tick's outputs (may be NULL). */
+int qpc_step_batch(qpc_controller*, int64_t B, double* q, double* v, const qpc_batch_in* in, const qpc_batch_out* out,
+                   double dt, int32_t nsteps, int32_t flags, void* stream);
+
 /* ---- stage-level entry points (parity tests; the tick above is their composition) -------------------------------- */
 /* kinematics + QP assembly only: writes the condensed QP of every instance (device or host pointers per flags):
  * P [B][n*n], qv [B][n], G [B][mg*n], lg/ug [B][mg], lb/ub [B][nbox], desired_out [B][ndes] */

@@ -57,7 +57,8 @@ SETUP_SYMBOLS = ["qpc_version", "qpc_last_error", "qpc_device_count", "qpc_defau
                  "qpc_add_contact", "qpc_set_contact_params", "qpc_add_task", "qpc_set_task_desired", "qpc_regularize",
                  "qpc_standing_setup", "qpc_set_settings", "qpc_finalize", "qpc_controller_dims"]
 COMPUTE_SYMBOLS = ["qpc_solve_batch", "qpc_reserve", "qpc_launch_count", "qpc_assemble_batch", "qpc_solve_qp_batch",
-                   "qpc_set_profiling", "qpc_stage_times", "qpc_measure_fp64_peak"]
+                   "qpc_set_profiling", "qpc_stage_times", "qpc_measure_fp64_peak", "qpc_set_warm_start",
+                   "qpc_reset_warm_start", "qpc_step_batch"]
 
 _libs = {}
 
@@ -250,6 +251,43 @@ class DeviceController:
         ms = (C.c_double * 3)()
         check(self.lib, self.lib.qpc_stage_times(self.h.ctrl, ms), "qpc_stage_times")
         return [ms[0], ms[1], ms[2]]
+
+    def set_warm_start(self, on: bool):
+        """OSQP's implicit warm start between ticks (previous x, y, rho of the same batch slot); off = cold starts."""
+        check(self.lib, self.lib.qpc_set_warm_start(self.h.ctrl, C.c_int32(int(on))), "qpc_set_warm_start")
+
+    def reset_warm_start(self):
+        check(self.lib, self.lib.qpc_reset_warm_start(self.h.ctrl), "qpc_reset_warm_start")
+
+    def step_host(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None):
+        """`nsteps` closed-loop ticks on the device (qpc_step_batch); returns (q, v, result of the last tick)."""
+        h = self.h
+        h.sync_defaults()
+        q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
+        q, v = q.copy(), v.copy()
+        res = _alloc_out(h, B)
+        bi, bo = h.batch_in(q, v, desired, cw, cm), _batch_out(res)
+        check(self.lib, self.lib.qpc_step_batch(h.ctrl, C.c_int64(B), C.c_void_p(q.ctypes.data),
+                                                C.c_void_p(v.ctypes.data), C.byref(bi), C.byref(bo), C.c_double(dt),
+                                                C.c_int32(nsteps), C.c_int32(HOST_PTRS), None), "qpc_step_batch")
+        return q, v, res
+
+    def step_device(self, B: int, q, v, dt: float, nsteps: int, out: Optional[dict] = None, contact_weight=None,
+                    contact_maxnormalforce=None, stream: int = 0):
+        """Closed-loop ticks on device tensors, in place and asynchronous on `stream`."""
+        ptr = lambda t: t.data_ptr()  # noqa: E731
+        bi = qpc_batch_in()
+        bi.q, bi.v = ptr(q), ptr(v)
+        bi.contact_weight = None if contact_weight is None else ptr(contact_weight)
+        bi.contact_maxnormalforce = None if contact_maxnormalforce is None else ptr(contact_maxnormalforce)
+        bi.contact_stride = 0 if contact_weight is None or contact_weight.dim() == 1 else contact_weight.shape[1]
+        bo = qpc_batch_out()
+        for name in ("tau", "vdot", "wrench", "status", "iters", "residuals", "factorizations"):
+            t = None if out is None else out.get(name)
+            setattr(bo, name, None if t is None else ptr(t))
+        check(self.lib, self.lib.qpc_step_batch(self.h.ctrl, C.c_int64(B), C.c_void_p(ptr(q)), C.c_void_p(ptr(v)),
+                                                C.byref(bi), C.byref(bo), C.c_double(dt), C.c_int32(nsteps),
+                                                C.c_int32(DEVICE_PTRS), C.c_void_p(stream)), "qpc_step_batch")
 
     def solve_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None) -> BatchResult:
         """Host numpy buffers in, host numpy buffers out (H2D + kernels + D2H inside the call)."""

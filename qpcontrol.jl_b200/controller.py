@@ -112,6 +112,25 @@ class MomentumBasedController:
         return res
 
 
+    def set_warm_start(self, on: bool = True):
+        """Sequential ticks start from the previous tick's iterates and rho of the same batch slot, as the reference's
+        single OSQP workspace does between `solve!` calls (momentum.jl:58)."""
+        self.finalize().set_warm_start(on)
+
+    def reset_warm_start(self):
+        self.finalize().reset_warm_start()
+
+    def simulate(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None,
+                 check: bool = True):
+        """Closed loop of `nsteps` control ticks at period `dt` for B instances, on the device
+        (notebooks/Standing controller.ipynb:202-214 batched; see qpc_step_batch).  Returns (q, v, last BatchResult)."""
+        dev = self.finalize()
+        q, v, res = dev.step_host(q, v, dt, nsteps, desired, contact_weight, contact_maxnormalforce)
+        if check:
+            checkstatus(res.status)
+        return q, v, res
+
+
 class StandingController:
     """reference `src/highlevel/standing.jl`.  `feet` / `pelvis` are body indices, `nominal_q` the nominal
     configuration; keyword defaults are the reference's (:23-29)."""
@@ -162,6 +181,10 @@ class StandingController:
         """PD laws for CoM / pelvis / joints (standing.jl:60-85) are evaluated on the device, then the low-level
         controller runs (standing.jl:87)."""
         return self.lowlevel(q, v, None, contact_weight, contact_maxnormalforce, check=check)
+
+    def simulate(self, q, v, dt: float, nsteps: int, contact_weight=None, contact_maxnormalforce=None,
+                 check: bool = True):
+        return self.lowlevel.simulate(q, v, dt, nsteps, None, contact_weight, contact_maxnormalforce, check=check)
 
 
 def center_of_mass_host(mech: Mechanism, q: np.ndarray) -> np.ndarray:

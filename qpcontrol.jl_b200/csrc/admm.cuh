@@ -131,6 +131,10 @@ struct AdmmProblem {  // this instance's slots in global memory
   int *status, *iters;
   double* res;
   int* nfac = nullptr;
+  // warm start (optional): previous unscaled x [n], y [mg+nbx] and the rho they ended with (<= 0: start cold);
+  // rho_io receives this solve's final rho, or -1 when the solve was not accepted
+  const double *x0 = nullptr, *y0 = nullptr;
+  double* rho_io = nullptr;
 };
 
 // out[j] = sum_i Gs[i][j] w[i] (+ box term), j < n : one thread group per column, conflict-free column walks
@@ -343,6 +347,14 @@ QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg
   }
   QPC_SYNC();
   double rho = st.rho;
+  if (pb.rho_io && pb.x0 && pb.y0 && *pb.rho_io > 0.0) {  // OSQP's implicit warm start (see admm_reg.cuh)
+    rho = *pb.rho_io;
+    for (int j = tid; j < n; j += nt) s.x[j] = pb.x0[j] / s.D[j];
+    for (int i = tid; i < m; i += nt) s.y[i] = pb.y0[i] * c / s.E[i];
+    QPC_SYNC();
+    admm_A_times(s, n, mg, nbx, s.x, s.z);
+    QPC_SYNC();
+  }
   admm_set_rho(s, m, rho);
   admm_factor(s, pb.P, n, mg, nbx, c, st.sigma, false);
   for (int i = tid; i < m; i += nt) s.w[i] = s.rho[i] * s.z[i] - s.y[i];
@@ -543,6 +555,7 @@ QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg
     *pb.status = status;
     if (pb.iters) *pb.iters = iter;
     if (pb.nfac) *pb.nfac = nfac;
+    if (pb.rho_io) *pb.rho_io = (status == 1 || status == 2) ? rho : -1.0;
     if (pb.res) {
       pb.res[0] = pri_res;
       pb.res[1] = dua_res;

@@ -29,6 +29,9 @@
 
 namespace qpc {
 
+#ifndef QPC_REG_PARK
+#define QPC_REG_PARK 10
+#endif
 constexpr int REG_MAXW = 16;  // warps per CTA supported by the reduction scratch
 constexpr int REG_TR = 4;     // rows per thread
 
@@ -105,6 +108,21 @@ __device__ __forceinline__ double group_reduce(const double (&s)[REG_TR], int q)
   double v = comb(k, __shfl_xor_sync(0xffffffffu, o, NB / 4));
 #pragma unroll
   for (int d = NB / 8; d > 0; d >>= 1) v = comb(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+// the same transpose-reduction for unsigned maxima (Ruiz norms on high words)
+template <int NB>
+__device__ __forceinline__ unsigned group_reduce_umax(const unsigned (&s)[REG_TR], int q) {
+  const bool hiA = q & (NB / 2), hiB = q & (NB / 4);
+  const unsigned k0 = hiA ? s[2] : s[0], k1 = hiA ? s[3] : s[1];
+  const unsigned o0 = hiA ? s[0] : s[2], o1 = hiA ? s[1] : s[3];
+  const unsigned r0 = max(k0, __shfl_xor_sync(0xffffffffu, o0, NB / 2));
+  const unsigned r1 = max(k1, __shfl_xor_sync(0xffffffffu, o1, NB / 2));
+  const unsigned k = hiB ? r1 : r0, o = hiB ? r0 : r1;
+  unsigned v = max(k, __shfl_xor_sync(0xffffffffu, o, NB / 4));
+#pragma unroll
+  for (int d = NB / 8; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
   return v;
 }
 
@@ -412,37 +430,47 @@ struct RegSolver {
     __syncthreads();
     load_tile();
     // ---- Ruiz equilibration of [P A'; A 0]; A = [G; E_box] -----------------------------------------
+    // Lazy form: the tile stays unscaled during the `scaling` passes; the accumulated scaling S of every position lives
+    // in shared memory and the scaled magnitudes |a_ij| S_j are formed on the fly (one multiply per element and pass;
+    // S_i is a common factor of the row).  Norms are maxima of the high words of those magnitudes (integer max,
+    // relative truncation < 2^-20: any positive scaling is admissible, the one actually used is tracked exactly).
+    // The cost scaling c applies to the P block only, so every row keeps two maxima: over the constraint columns and
+    // over the x columns.  The x-column maximum of an x row is also the P-block column norm the cost scaling needs.
     double cscale = 1.0;
-    double* sv = cv;  // scale vector broadcast, NP entries
-    for (int it = 0; it < st.scaling; it++) {
-      double nr4[TR];
+    double* sv = cv;  // accumulated scaling of every position, NP entries, written by the row owners
+    double S = 1.0;   // accumulated scaling of the owned row (= D for x rows, E for general rows)
+    if (h == 0) sv[row] = 1.0;
+    __syncthreads();
+    unsigned mgm = 0, mxm = 0;  // high words of max_j |a_ij| S_j over constraint columns / x columns, owned row
+    auto scaled_maxima = [&]() {
+      double dcol[TC];
+      load_vec<TC>(sv + c0, dcol);
+      unsigned g4[TR], x4[TR];
 #pragma unroll
-      for (int r = 0; r < TR; r++) {
-        double v = 0.0;
+      for (int r = 0; r < TR; r++) g4[r] = x4[r] = 0u;
 #pragma unroll
-        for (int c = 0; c < TC; c++) {
-          const double t = fabs(a[r][c]);
-          v = t > v ? t : v;
+      for (int c = 0; c < TC; c++) {
+        const bool xc = c0 + c >= mg;
+#pragma unroll
+        for (int r = 0; r < TR; r++) {
+          const unsigned hw = (unsigned)__double2hiint(a[r][c] * dcol[c]) & 0x7fffffffu;
+          g4[r] = max(g4[r], xc ? 0u : hw);
+          x4[r] = max(x4[r], xc ? hw : 0u);
         }
-        nr4[r] = v;
       }
-      double nr = group_reduce<true, NB>(nr4, q);
+      mgm = group_reduce_umax<NB>(g4, q);
+      mxm = group_reduce_umax<NB>(x4, q);
+    };
+    if (st.scaling > 0) scaled_maxima();
+    __syncthreads();  // every warp has read sv before the first pass overwrites it
+    for (int it = 0; it < st.scaling; it++) {
+      const double ng = S * __hiloint2double((int)mgm, 0), nx = S * __hiloint2double((int)mxm, 0);
+      double nr = isx ? fmax(ng, cscale * nx) : fmax(ng, nx);
       if (hasbox) nr = fmax(nr, fabs(cb));
       const double sr = row < NK ? 1.0 / sqrt(limit_scaling(nr)) : 1.0;
       const double eb = hasbox ? 1.0 / sqrt(limit_scaling(fabs(cb))) : 1.0;
-      if (h == 0) sv[row] = sr;
-      __syncthreads();
-      {
-        double sc4[TR];
-#pragma unroll
-        for (int r = 0; r < TR; r++) sc4[r] = sv[4 * g + r];
-#pragma unroll
-        for (int c = 0; c < TC; c++) {
-          const double scol = sv[c0 + c];
-#pragma unroll
-          for (int r = 0; r < TR; r++) a[r][c] *= sc4[r] * scol;
-        }
-      }
+      S *= sr;
+      if (h == 0) sv[row] = S;
       if (isx) {
         qs *= sr;
         D *= sr;
@@ -453,37 +481,33 @@ struct RegSolver {
       } else if (isg) {
         E *= sr;
       }
+      __syncthreads();
+      scaled_maxima();
       // cost scaling: mean column norm of P_bar (= row norms of the x block, by symmetry) vs |q_bar|_inf
-      double pn4[TR];
-#pragma unroll
-      for (int r = 0; r < TR; r++) {
-        double v = 0.0;
-        const bool xr = 4 * g + r >= mg;
-#pragma unroll
-        for (int c = 0; c < TC; c++)
-          if (xr && c0 + c >= mg) {
-            const double t = fabs(a[r][c]);
-            v = t > v ? t : v;
-          }
-        pn4[r] = v;
-      }
-      const double pn = group_reduce<true, NB>(pn4, q);
       double v2[2];
       v2[0] = isx ? fabs(qs) : 0.0;
-      v2[1] = (isx && h == 0) ? pn : 0.0;
+      v2[1] = (isx && h == 0) ? cscale * S * __hiloint2double((int)mxm, 0) : 0.0;
       reg_block_reduce<1, 1>(v2, red, redsel);
       double ct = limit_scaling(n > 0 ? v2[1] / n : 1.0);
       const double qn = limit_scaling(v2[0]);
       ct = 1.0 / fmax(ct, qn);
-#pragma unroll
-      for (int r = 0; r < TR; r++) {
-        const bool xr = 4 * g + r >= mg;
-#pragma unroll
-        for (int c = 0; c < TC; c++)
-          if (xr && c0 + c >= mg) a[r][c] *= ct;
-      }
       if (isx) qs *= ct;
       cscale *= ct;
+    }
+    if (st.scaling > 0) {  // apply: a_ij <- S_i S_j a_ij, times c on the P block
+      double dcol[TC], srow[TR];
+      load_vec<TC>(sv + c0, dcol);
+#pragma unroll
+      for (int r = 0; r < TR; r++) srow[r] = sv[4 * g + r];
+#pragma unroll
+      for (int c = 0; c < TC; c++) {
+        const bool xc = c0 + c >= mg;
+#pragma unroll
+        for (int r = 0; r < TR; r++) {
+          const double f = (xc && 4 * g + r >= mg) ? cscale * srow[r] : srow[r];
+          a[r][c] *= f * dcol[c];
+        }
+      }
     }
     l *= E;
     u *= E;
@@ -494,6 +518,15 @@ struct RegSolver {
     double* CD = &sc(11, 0);                    // 0 cscale | 1 1/cscale | 2 rho | 3 pri_res | 4 dua_res
     int* CI = reinterpret_cast<int*>(CD + 8);   // 0 status | 1 iter | 2 nfac | 3 next check | 4 next adapt | 5 refactor | 6 done
     const int chk_iv = st.check_termination, ada_iv = (st.adaptive_rho && st.adaptive_rho_interval) ? st.adaptive_rho_interval : 0;
+    // Warm start = OSQP's implicit warm start between the solves of one workspace: x, y and rho of
+    // the previous tick of this batch slot; a slot whose last solve was not accepted (rho_io <= 0) starts cold.
+    double rho_start = st.rho;
+    bool warm = false;
+    if (pb_.rho_io && pb_.x0 && pb_.y0) {
+      const double r = *pb_.rho_io;
+      warm = r > 0.0;
+      if (warm) rho_start = r;
+    }
     if (h == 0) {
       sc(0, row) = qs;
       sc(1, row) = l;
@@ -501,12 +534,12 @@ struct RegSolver {
       sc(3, row) = cb;
       sc(6, row) = isx ? D : E;
       sc(7, row) = E;
-      set_rho(st.rho);
+      set_rho(rho_start);
     }
     if (tid == 0) {
       CD[0] = cscale;
       CD[1] = 1.0 / cscale;
-      CD[2] = st.rho;
+      CD[2] = rho_start;
       CD[3] = CD[4] = 0.0;
       CI[0] = -10;
       CI[1] = 0;
@@ -517,8 +550,22 @@ struct RegSolver {
       CI[6] = 0;
     }
     __syncthreads();
+    if (warm) {  // x_bar = D^-1 x, y_bar = c E^-1 y, z = A x_bar (unprojected, as osqp_warm_start does)
+      if (isx) x = pb_.x0[xi] / D;
+      double yw = 0.0;
+      if (isg) yw = pb_.y0[row] * cscale / E;
+      else if (hasbox) yw = pb_.y0[mg + xi - (n - nbx)] * cscale / E;
+      yr = yw * sc(5, row);
+      if (h == 0) cv[row] = isx ? x : 0.0;
+      __syncthreads();
+      const double gx = k0_product(cv);
+      z = isg ? gx : (hasbox ? cb * x : 0.0);
+      __syncthreads();
+    }
     // ---- iterations ------------------------------------------------------------------------------------------------------
     const double alpha = st.alpha, sigma = st.sigma, oma = 1.0 - st.alpha;
+    constexpr int PARK = QPC_REG_PARK < TR * TC ? QPC_REG_PARK : TR * TC;
+    volatile double park[PARK > 0 ? PARK : 1];
     for (;;) {
       if (CI[6]) break;
       int iter = CI[1];
@@ -551,6 +598,11 @@ struct RegSolver {
         sc(10, row) = sc(4, row) * yr;
       }
       iterate(uv + (iter & 1) * US, uv + ((iter + 1) & 1) * US, alpha, oma, sigma);
+      // Manual live-range split: the residual check below never touches the tile but needs ~45 registers of its own;
+      // left alone, ptxas spills tile entries for the whole solve and reloads them inside the plain-iteration loop
+      // (8 LDL.64 per iteration).  Parking PARK entries in local memory across the check keeps the loop spill-free.
+#pragma unroll
+      for (int i = 0; i < PARK; i++) park[i] = a[i / TC][i % TC];
       const double y = sc(4, row) * yr;
       if (h == 0) {
         cv[row] = isx ? x : 0.0;
@@ -700,6 +752,8 @@ struct RegSolver {
         CI[5] = refactor ? 1 : 0;
         CI[6] = done ? 1 : 0;
       }
+#pragma unroll
+      for (int i = 0; i < PARK; i++) a[i / TC][i % TC] = park[i];
       __syncthreads();
     }
     // ---- unscale and store -----------------------------------------------------------------------------------------------
@@ -716,6 +770,7 @@ struct RegSolver {
       *pb_.status = CI[0];
       if (pb_.iters) *pb_.iters = CI[1];
       if (pb_.nfac) *pb_.nfac = CI[2];
+      if (pb_.rho_io) *pb_.rho_io = (CI[0] == 1 || CI[0] == 2) ? CD[2] : -1.0;
       if (pb_.res) {
         pb_.res[0] = CD[3];
         pb_.res[1] = CD[4];

@@ -12,6 +12,7 @@ struct DeviceBuffers {
   // QP workspace (both pointer modes)
   double *P = nullptr, *qv = nullptr, *G = nullptr, *lg = nullptr, *ug = nullptr, *lb = nullptr, *ub = nullptr;
   double *des = nullptr, *x = nullptr, *y = nullptr;
+  double* rho = nullptr;  // [capB] rho every slot ended its last accepted solve with (<= 0: none) -- warm start
   // staging for QPC_HOST_PTRS
   double *q = nullptr, *v = nullptr, *desired = nullptr, *cw = nullptr, *cm = nullptr;
   double *tau = nullptr, *vdot = nullptr, *wrench = nullptr, *res = nullptr;
@@ -27,6 +28,7 @@ struct Backend {
   std::atomic<long long> launches{0};
   std::mutex mu;
   bool profiling = false;
+  bool warm_start = false;  // qpc_set_warm_start
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int* d_nfac = nullptr;  // [capB] factorisations per instance
   // chunked tick: sub-batches go to side streams so that one chunk's assembly / inverse dynamics and the tail of its
@@ -93,6 +95,11 @@ qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long bas
     pb.iters = qb.iters ? qb.iters + inst : nullptr;
     pb.res = qb.res ? qb.res + 2 * inst : nullptr;
     pb.nfac = qb.nfac ? qb.nfac + inst : nullptr;
+    if (qb.warm) {
+      pb.x0 = pb.x;
+      pb.y0 = pb.y;
+      pb.rho_io = qb.rho + inst;
+    }
     admm_solve(st, pb, n, mg, nbx, smem, gmat);
   }
 }
@@ -104,7 +111,10 @@ struct RegTraits {
   // Registers per thread, chosen against the 16K registers of each SM sub-partition (warps of all resident CTAs are
   // spread over the four of them): NB = 16, TC = 5 -> 320 threads, 2 CTAs/SM = 5 warps per sub-partition -> 96;
   // NB = 8: 128 -> 3 CTAs of 160 threads (TC = 10), 4 of 128 (TC = 8); larger tiles run 1 CTA per SM.
-  static constexpr int MAXREG = NB == 16 ? 96 : (TC <= 10 ? 128 : (TC <= 14 ? 255 : 240));
+#ifndef QPC_REG_SMALL_TILE
+#define QPC_REG_SMALL_TILE 128
+#endif
+  static constexpr int MAXREG = NB == 16 ? 96 : (TC <= 10 ? QPC_REG_SMALL_TILE : (TC <= 14 ? 255 : 240));
 };
 template <int TC, int NB>
 __global__ void __launch_bounds__((RegTraits<TC, NB>::MAXT)) __maxnreg__((RegTraits<TC, NB>::MAXREG))
@@ -125,6 +135,11 @@ qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long
     pb.iters = qb.iters ? qb.iters + inst : nullptr;
     pb.res = qb.res ? qb.res + 2 * inst : nullptr;
     pb.nfac = qb.nfac ? qb.nfac + inst : nullptr;
+    if (qb.warm) {
+      pb.x0 = pb.x;
+      pb.y0 = pb.y;
+      pb.rho_io = qb.rho + inst;
+    }
     RegSolver<TC, NB> s;
     s.n = n;
     s.mg = mg;
@@ -183,6 +198,8 @@ static int ensure_capacity(qpc_controller* c, long long B, long long dstride, lo
     CUDA_TRY(grow(b.des, B * p.ndes));
     CUDA_TRY(grow(b.x, B * n));
     CUDA_TRY(grow(b.y, B * (mg + nbx)));
+    CUDA_TRY(grow(b.rho, B));
+    CUDA_TRY(cudaMemset(b.rho, 0, sizeof(double) * (size_t)B));
     CUDA_TRY(grow(b.q, B * p.nq));
     CUDA_TRY(grow(b.v, B * p.nv));
     CUDA_TRY(grow(b.tau, B * p.nv));
@@ -330,6 +347,8 @@ static QpBuffers qp_view(const DeviceBuffers& b) {
   q.status = b.status;
   q.iters = b.iters;
   q.res = b.res;
+  q.rho = b.rho;
+  q.warm = 0;
   return q;
 }
 
@@ -352,6 +371,7 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
   if (iters) qb.iters = iters;
   if (res) qb.res = res;
   qb.nfac = nfac ? nfac : c->be.d_nfac;
+  qb.warm = c->be.warm_start ? 1 : 0;
   const bool prof = c->be.profiling;
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
   DeviceBuffers& hb = c->be.buf;
@@ -455,7 +475,7 @@ void qpc_controller_destroy(qpc_controller* c) {
     cudaSetDevice(c->be.device);
     DeviceBuffers& b = c->be.buf;
     void* ptrs[] = {b.P, b.qv, b.G, b.lg, b.ug, b.lb, b.ub, b.des, b.x, b.y, b.q, b.v, b.desired, b.cw,
-                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac};
+                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho};
     for (int i = 0; i < 4; i++)
       if (c->be.ev[i]) cudaEventDestroy(c->be.ev[i]);
     for (void* p : ptrs)
@@ -539,6 +559,159 @@ int qpc_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const 
   rc = run_tick(c, B, io, b.tau, b.vdot, b.wrench, b.status, b.iters, b.res, nullptr, s, &hx);
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(s));
+  return QPC_OK;
+}
+
+int qpc_set_warm_start(qpc_controller* c, int32_t on) {
+  if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
+  std::lock_guard<std::mutex> lock(c->be.mu);
+  c->be.warm_start = on != 0;
+  return QPC_OK;
+}
+
+int qpc_reset_warm_start(qpc_controller* c) {
+  if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
+  std::lock_guard<std::mutex> lock(c->be.mu);
+  CUDA_TRY(cudaSetDevice(c->be.device));
+  if (c->be.buf.rho && c->be.buf.capB > 0) {
+    CUDA_TRY(cudaMemsetAsync(c->be.buf.rho, 0, sizeof(double) * (size_t)c->be.buf.capB, c->be.stream));
+    CUDA_TRY(cudaStreamSynchronize(c->be.stream));
+  }
+  return QPC_OK;
+}
+
+// ---- closed loop: tick, then advance (q, v) in place with the commanded accelerations -------------------------------------
+// Semi-implicit Euler on the configuration manifold: v+ = v + dt vd; revolute / prismatic q+ = q + dt v+; quaternion
+// floating joint (q = (w,x,y,z,p), v = (omega, v) in body frame): quat+ = quat * exp(dt omega+ / 2), p+ = p + dt R v+.
+// Instances whose solve was rejected (checkstatus, momentum.jl:83-91) are left where they are.
+__global__ void qpc_integrate_kernel(const DevProgram* __restrict__ pg, double* q, double* v, const double* __restrict__ vdot,
+                                     const int* __restrict__ status, double dt, long long B) {
+  const long long inst = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (inst >= B) return;
+  if (status && status[inst] != 1 && status[inst] != 2) return;
+  const int nq = pg->nq, nv = pg->nv;
+  double* qi = q + inst * nq;
+  double* vi = v + inst * nv;
+  const double* vd = vdot + inst * nv;
+  for (int i = 0; i < nv; i++) vi[i] += dt * vd[i];
+  for (int b = 0; b < pg->nb; b++) {
+    const int jt = pg->jtype[b], qo = pg->qoff[b], vo = pg->voff[b];
+    if (jt == 0 || jt == 1) {
+      qi[qo] += dt * vi[vo];
+    } else if (jt == 2) {
+      double R[9];
+      quat_to_rot(qi[qo], qi[qo + 1], qi[qo + 2], qi[qo + 3], R);
+      const V3 om = ld3(vi + vo), vl = rot(R, ld3(vi + vo + 3));
+      const double th = sqrt(dot(om, om)) * dt;
+      const double hs = th > 1e-12 ? sin(0.5 * th) / th * dt : 0.5 * dt, hc = cos(0.5 * th);
+      const double ew = hc, ex = hs * om.x, ey = hs * om.y, ez = hs * om.z;
+      const double w0 = qi[qo], x0 = qi[qo + 1], y0 = qi[qo + 2], z0 = qi[qo + 3];
+      double w1 = w0 * ew - x0 * ex - y0 * ey - z0 * ez;
+      double x1 = w0 * ex + x0 * ew + y0 * ez - z0 * ey;
+      double y1 = w0 * ey - x0 * ez + y0 * ew + z0 * ex;
+      double z1 = w0 * ez + x0 * ey - y0 * ex + z0 * ew;
+      const double nrm = 1.0 / sqrt(w1 * w1 + x1 * x1 + y1 * y1 + z1 * z1);
+      qi[qo] = w1 * nrm;
+      qi[qo + 1] = x1 * nrm;
+      qi[qo + 2] = y1 * nrm;
+      qi[qo + 3] = z1 * nrm;
+      qi[qo + 4] += dt * vl.x;
+      qi[qo + 5] += dt * vl.y;
+      qi[qo + 6] += dt * vl.z;
+    }
+  }
+}
+
+int qpc_step_batch(qpc_controller* c, int64_t B, double* q, double* v, const qpc_batch_in* in, const qpc_batch_out* out,
+                   double dt, int32_t nsteps, int32_t flags, void* stream_) {
+  if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
+  if (!q || !v || B < 0 || nsteps < 0 || !(dt > 0.0)) return qpc_fail(QPC_ERR_ARG, "qpc_step_batch: bad arguments");
+  if (B == 0 || nsteps == 0) return QPC_OK;
+  const DevProgram& p = c->prog;
+  const double* desired = in ? in->desired : nullptr;
+  const double *cwt = in ? in->contact_weight : nullptr, *cmx = in ? in->contact_maxnormalforce : nullptr;
+  const long long dstride = desired ? in->desired_stride : 0, cstride = cwt ? in->contact_stride : 0;
+  if (desired && dstride != 0 && dstride < p.ndes)
+    return qpc_fail(QPC_ERR_ARG, "desired_stride smaller than the number of desired values");
+  if ((cwt == nullptr) != (cmx == nullptr))
+    return qpc_fail(QPC_ERR_ARG, "contact_weight and contact_maxnormalforce must be given together");
+  if (cwt && cstride != 0 && cstride < p.ncontacts)
+    return qpc_fail(QPC_ERR_ARG, "contact_stride smaller than the number of contacts");
+  std::lock_guard<std::mutex> lock(c->be.mu);
+  CUDA_TRY(cudaSetDevice(c->be.device));
+  if (c->be.dirty) {
+    int rc = upload_program(c);
+    if (rc) return rc;
+  }
+  int rc = ensure_capacity(c, B, desired ? (dstride ? dstride : p.ndes) : 0, cwt ? (cstride ? cstride : p.ncontacts) : 0);
+  if (rc) return rc;
+  DeviceBuffers& b = c->be.buf;
+  const bool host = flags != QPC_DEVICE_PTRS;
+  cudaStream_t s = host ? c->be.stream : (cudaStream_t)stream_;
+  BatchIO io;
+  io.desired_stride = dstride;
+  io.contact_stride = cstride;
+  double *dq = q, *dv = v;
+  io.desired = desired;
+  io.cweight = cwt;
+  io.cmaxnf = cmx;
+  qpc_batch_out o;
+  memset(&o, 0, sizeof(o));
+  if (out) o = *out;
+  if (host) {
+    dq = b.q;
+    dv = b.v;
+    CUDA_TRY(cudaMemcpyAsync(dq, q, sizeof(double) * (size_t)B * p.nq, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dv, v, sizeof(double) * (size_t)B * p.nv, cudaMemcpyHostToDevice, s));
+    if (desired) {
+      CUDA_TRY(cudaMemcpyAsync(b.desired, desired, sizeof(double) * (size_t)(dstride ? B * dstride : p.ndes),
+                               cudaMemcpyHostToDevice, s));
+      io.desired = b.desired;
+    }
+    if (cwt) {
+      const size_t cnt = (size_t)(cstride ? B * cstride : p.ncontacts);
+      CUDA_TRY(cudaMemcpyAsync(b.cw, cwt, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(b.cm, cmx, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+      io.cweight = b.cw;
+      io.cmaxnf = b.cm;
+    }
+    o.tau = b.tau;
+    o.vdot = b.vdot;
+    o.wrench = b.wrench;
+    o.status = b.status;
+    o.iters = b.iters;
+    o.residuals = b.res;
+    o.factorizations = nullptr;
+  }
+  io.q = dq;
+  io.v = dv;
+  double* vdot = o.vdot ? o.vdot : b.vdot;
+  int* status = o.status ? o.status : b.status;
+  const DevProgram* dp = (const DevProgram*)c->be.d_prog;
+  for (int k = 0; k < nsteps; k++) {
+    rc = run_tick(c, B, io, o.tau, vdot, o.wrench, status, o.iters, o.residuals, o.factorizations, s);
+    if (rc) return rc;
+    qpc_integrate_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(dp, dq, dv, vdot, status, dt, B);
+    c->be.launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (host) {
+    const size_t nb_ = (size_t)B;
+    CUDA_TRY(cudaMemcpyAsync(q, dq, sizeof(double) * nb_ * p.nq, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(v, dv, sizeof(double) * nb_ * p.nv, cudaMemcpyDeviceToHost, s));
+    if (out) {
+      const int nc6 = p.ncontacts * 6;
+      if (out->tau) CUDA_TRY(cudaMemcpyAsync(out->tau, b.tau, sizeof(double) * nb_ * p.nv, cudaMemcpyDeviceToHost, s));
+      if (out->vdot) CUDA_TRY(cudaMemcpyAsync(out->vdot, b.vdot, sizeof(double) * nb_ * p.nv, cudaMemcpyDeviceToHost, s));
+      if (out->wrench) CUDA_TRY(cudaMemcpyAsync(out->wrench, b.wrench, sizeof(double) * nb_ * nc6, cudaMemcpyDeviceToHost, s));
+      if (out->status) CUDA_TRY(cudaMemcpyAsync(out->status, b.status, sizeof(int) * nb_, cudaMemcpyDeviceToHost, s));
+      if (out->iters) CUDA_TRY(cudaMemcpyAsync(out->iters, b.iters, sizeof(int) * nb_, cudaMemcpyDeviceToHost, s));
+      if (out->residuals) CUDA_TRY(cudaMemcpyAsync(out->residuals, b.res, sizeof(double) * 2 * nb_, cudaMemcpyDeviceToHost, s));
+      if (out->factorizations)
+        CUDA_TRY(cudaMemcpyAsync(out->factorizations, c->be.d_nfac, sizeof(int) * nb_, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
   return QPC_OK;
 }
 

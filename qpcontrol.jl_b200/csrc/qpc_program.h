@@ -87,6 +87,8 @@ struct QpBuffers {
   int *status, *iters;
   double* res;  // [B][2]
   int* nfac;    // [B] number of factorisations (1 + rho updates), optional
+  double* rho;  // [B] final rho of the slot's last accepted solve (<= 0: none); read when `warm`
+  int warm;     // OSQP's implicit warm start: start from x, y, rho of the previous tick of the same slot
 };
 
 }  // namespace qpc

@@ -64,9 +64,20 @@ int emu_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
   return QPC_OK;
 }
 
+// rho_io != NULL: warm start -- x, y hold the previous solution on entry, rho_io the rho it ended with (<= 0: cold)
+int emu_solve_qp_batch_warm(int64_t B, int32_t n, int32_t mg, int32_t nbox, const double* P, const double* qv,
+                            const double* G, const double* lg, const double* ug, const double* lb, const double* ub,
+                            const qpc_settings* st, double* x, double* y, int32_t* status, int32_t* iters, double* res,
+                            double* rho_io);
 int emu_solve_qp_batch(int64_t B, int32_t n, int32_t mg, int32_t nbox, const double* P, const double* qv,
                        const double* G, const double* lg, const double* ug, const double* lb, const double* ub,
                        const qpc_settings* st, double* x, double* y, int32_t* status, int32_t* iters, double* res) {
+  return emu_solve_qp_batch_warm(B, n, mg, nbox, P, qv, G, lg, ug, lb, ub, st, x, y, status, iters, res, nullptr);
+}
+int emu_solve_qp_batch_warm(int64_t B, int32_t n, int32_t mg, int32_t nbox, const double* P, const double* qv,
+                            const double* G, const double* lg, const double* ug, const double* lb, const double* ub,
+                            const qpc_settings* st, double* x, double* y, int32_t* status, int32_t* iters, double* res,
+                            double* rho_io) {
   Settings s;
   qpc_copy_settings(st, s);
 #pragma omp parallel
@@ -87,6 +98,11 @@ int emu_solve_qp_batch(int64_t B, int32_t n, int32_t mg, int32_t nbox, const dou
       pb.status = status + i;
       pb.iters = iters ? iters + i : nullptr;
       pb.res = res ? res + 2 * i : nullptr;
+      if (rho_io && y) {
+        pb.x0 = pb.x;
+        pb.y0 = pb.y;
+        pb.rho_io = rho_io + i;
+      }
       if (n == 0) {
         *pb.status = 1;
         if (pb.iters) *pb.iters = 0;

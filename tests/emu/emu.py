@@ -55,7 +55,8 @@ class EmuController:
         return out
 
 
-def solve_qp_batch(P, qv, G, lg, ug, lb=None, ub=None, settings=None):
+def solve_qp_batch(P, qv, G, lg, ug, lb=None, ub=None, settings=None, warm=None):
+    """`warm` = dict(x, y, rho) of a previous solve: OSQP-style warm start (updated in place)."""
     lib = L.load(build())
     P, qv, G, lg, ug = (L._c(a) for a in (P, qv, G, lg, ug))
     B, n = qv.shape
@@ -68,7 +69,11 @@ def solve_qp_batch(P, qv, G, lg, ug, lb=None, ub=None, settings=None):
     out = dict(x=np.zeros((B, n)), y=np.zeros((B, mg + nbox)), status=np.zeros(B, np.int32),
                iters=np.zeros(B, np.int32), res=np.zeros((B, 2)))
     p = L._p
-    L.check(lib, lib.emu_solve_qp_batch(C.c_int64(B), C.c_int32(n), C.c_int32(mg), C.c_int32(nbox), p(P), p(qv), p(G),
-                                        p(lg), p(ug), p(lb), p(ub), C.byref(st), p(out["x"]), p(out["y"]),
-                                        p(out["status"]), p(out["iters"]), p(out["res"])), "emu_solve_qp_batch")
+    out["rho"] = np.zeros(B)
+    if warm is not None:
+        out["x"][:], out["y"][:], out["rho"][:] = warm["x"], warm["y"], warm["rho"]
+    L.check(lib, lib.emu_solve_qp_batch_warm(C.c_int64(B), C.c_int32(n), C.c_int32(mg), C.c_int32(nbox), p(P), p(qv),
+                                             p(G), p(lg), p(ug), p(lb), p(ub), C.byref(st), p(out["x"]), p(out["y"]),
+                                             p(out["status"]), p(out["iters"]), p(out["res"]), p(out["rho"])),
+            "emu_solve_qp_batch_warm")
     return out
