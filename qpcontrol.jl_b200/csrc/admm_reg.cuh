@@ -319,15 +319,32 @@ struct RegSolver {
   //   v = zr + yr, z+ = clip(v), yr+ = v - z+, next rhs (general row) = z+ - yr+.
   __device__ __forceinline__ void iterate(const double* __restrict__ vec, double* __restrict__ nxt, double alpha,
                                           double oma, double sigma) {
-    double u[TC];
-    load_vec<TC>(vec + c0, u);
     double s0[TR];
 #pragma unroll
     for (int r = 0; r < TR; r++) s0[r] = 0.0;
+    if constexpr (TC % 2 == 0 && TC >= 6) {
+      // software pipeline over 16-byte chunks of the vector, two loads in flight ahead of the DFMAs that consume them
+      const double2* v2 = reinterpret_cast<const double2*>(vec + c0);
+      double2 ua = v2[0], ub = v2[1], uc = v2[2];
 #pragma unroll
-    for (int c = 0; c < TC; c++) {
+      for (int k = 0; k < TC / 2; k++) {
+        const double2 un = (k + 3 < TC / 2) ? v2[k + 3] : ua;
 #pragma unroll
-      for (int r = 0; r < TR; r++) s0[r] = fma(a[r][c], u[c], s0[r]);
+        for (int r = 0; r < TR; r++) s0[r] = fma(a[r][2 * k], ua.x, s0[r]);
+#pragma unroll
+        for (int r = 0; r < TR; r++) s0[r] = fma(a[r][2 * k + 1], ua.y, s0[r]);
+        ua = ub;
+        ub = uc;
+        uc = un;
+      }
+    } else {
+      double u[TC];
+      load_vec<TC>(vec + c0, u);
+#pragma unroll
+      for (int c = 0; c < TC; c++) {
+#pragma unroll
+        for (int r = 0; r < TR; r++) s0[r] = fma(a[r][c], u[c], s0[r]);
+      }
     }
     // everything that does not depend on the solve result is fetched / computed before the shuffle reduction
     const double rinv = sc(5, row), lo = sc(1, row), up = sc(2, row), cb = sc(3, row), qs = sc(0, row),

@@ -17,7 +17,7 @@ import RigidBodyDynamics: Mechanism, RigidBody, Joint, bodies, joints, tree_join
 export MomentumBasedController, StandingController, ContactPoint, OSQPSettings, QPSolveFailure,
     SpatialAccelerationTask, AngularAccelerationTask, LinearAccelerationTask, PointAccelerationTask,
     JointAccelerationTask, MomentumRateTask, LinearMomentumRateTask,
-    addtask!, addcontact!, regularize!, setdesired!, disable!, checkstatus
+    addtask!, addcontact!, regularize!, setdesired!, disable!, checkstatus, warmstart!, resetwarmstart!, simulate!
 
 const LIB = Ref{String}(get(ENV, "QPCONTROL_B200_LIB", "libqpcontrol_b200"))
 
@@ -242,6 +242,37 @@ function (c::MomentumBasedController)(tau::Matrix{Float64}, t::Number, q::Matrix
     end
     check && checkstatus(status)
     vdot, wrench, status
+end
+
+# ---- sequential ticks (SURVEY.md 8(f) rank 1) -----------------------------------------------------------------------------
+# The reference solves every tick in one OSQP workspace, so each `solve!` (momentum.jl:58) starts from the previous
+# tick's iterates and adapted rho.  warmstart!(controller, true) gives every batch column that behaviour.
+function warmstart!(c::MomentumBasedController, on::Bool=true)
+    c.initialized || initialize!(c)
+    check(ccall((:qpc_set_warm_start, LIB[]), Cint, (Ptr{Cvoid}, Int32), c.handle, on ? 1 : 0), "qpc_set_warm_start")
+end
+resetwarmstart!(c::MomentumBasedController) =
+    check(ccall((:qpc_reset_warm_start, LIB[]), Cint, (Ptr{Cvoid},), c.handle), "qpc_reset_warm_start")
+
+# `nsteps` closed-loop control ticks of period dt for B robots on the device: the batched counterpart of
+# simulate(state, T, PeriodicController(tau, dt, controller)) (notebooks/Standing controller.ipynb:202-214) under the
+# contact model the controller itself assumes.  q (nq x B) and v (nv x B) are advanced in place.
+function simulate!(c::MomentumBasedController, q::Matrix{Float64}, v::Matrix{Float64}, dt::Float64, nsteps::Integer;
+                   check::Bool=true)
+    c.initialized || initialize!(c)
+    B = size(q, 2)
+    nc = length(c.contacts)
+    tau = zeros(size(v)); vdot = similar(v); wrench = zeros(6, nc, B); status = zeros(Int32, B)
+    GC.@preserve q v tau vdot wrench status begin
+        bin = qpc_batch_in(C_NULL, C_NULL, C_NULL, 0, C_NULL, C_NULL, 0)
+        bout = qpc_batch_out(pointer(tau), pointer(vdot), pointer(wrench), pointer(status), C_NULL, C_NULL, C_NULL)
+        QPControlB200.check(ccall((:qpc_step_batch, LIB[]), Cint,
+                                  (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ref{qpc_batch_in}, Ref{qpc_batch_out},
+                                   Cdouble, Int32, Int32, Ptr{Cvoid}),
+                                  c.handle, B, q, v, bin, bout, dt, nsteps, 0, C_NULL), "qpc_step_batch")
+    end
+    check && checkstatus(status)
+    tau, vdot, wrench, status
 end
 
 # ---- StandingController (reference src/highlevel/standing.jl:18-56); the PD laws of :58-85 run on the device ---------
