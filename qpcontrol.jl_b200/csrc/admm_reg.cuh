@@ -346,11 +346,16 @@ struct RegSolver {
         for (int r = 0; r < TR; r++) s0[r] = fma(a[r][c], u[c], s0[r]);
       }
     }
-    // everything that does not depend on the solve result is fetched / computed before the shuffle reduction
+    // Everything that does not depend on the solve result t is fetched / computed before the shuffle reduction, and the
+    // update is arranged so that the chain after t is short:  v = alpha zt + (1 - alpha) z + yr  with
+    // zt = t / rho + (z - yr) (general row) or cb t (box row)  becomes one FMA  v = t k1 + c1;  then z+ = clip(v),
+    // yr+ = v - z+, and the next right-hand side needs  z+ - yr+ = 2 z+ - v.
     const double rinv = sc(5, row), lo = sc(1, row), up = sc(2, row), cb = sc(3, row), qs = sc(0, row),
                  cbrho = sc(12, row);
     const double w = z - yr, oz = oma * z, ox = oma * x;
-    asm volatile("" ::"d"(rinv), "d"(lo), "d"(up), "d"(cb), "d"(qs), "d"(cbrho), "d"(w), "d"(oz), "d"(ox));
+    const double k1 = alpha * (isg ? rinv : cb);
+    const double c1 = (isg ? fma(alpha, w, oz) : oz) + yr;
+    asm volatile("" ::"d"(lo), "d"(up), "d"(qs), "d"(cbrho), "d"(k1), "d"(c1), "d"(ox));
     const double t = -group_reduce<false, NB>(s0, q);
     double rhs = 0.0, rw = 0.0;
     if (isx) {
@@ -358,14 +363,12 @@ struct RegSolver {
       rhs = fma(sigma, x, -qs);
     }
     if (hasc) {
-      const double zt = isg ? fma(t, rinv, w) : cb * t;
-      const double zr = fma(alpha, zt, oz);
-      const double v = zr + yr;
+      const double v = fma(t, k1, c1);
       double zn = v < lo ? lo : v;
       zn = zn > up ? up : zn;
       yr = v - zn;
       z = zn;
-      rw = zn - yr;
+      rw = fma(2.0, zn, -v);
     }
     if (isg) rhs = rw;
     else if (hasbox) rhs = fma(cbrho, rw, rhs);
