@@ -261,6 +261,7 @@ def main():
     iters = out["iters"].cpu().numpy().astype(np.float64)
     nfac = out["factorizations"].cpu().numpy().astype(np.float64)
     accepted = float(np.mean((status == 1) | (status == 2)))
+    tau_first = out["tau"][:min(args.cpu_sample, B)].cpu().numpy()  # compared with the CPU arm below
 
     # ---- end to end through the host-pointer C-ABI call ("e2e") ---------------------------------------------------------
     hq = torch.from_numpy(q).pin_memory()
@@ -391,7 +392,7 @@ def main():
                                     "kind": "port", "sample": f"first {sample} instances of rank 0's batch, "
                                     "oracle/ lifted sparse-LDL OSQP restatement, OpenMP over instances, cold start",
                                     "iters_mean": float(r["iters"].mean())}
-            tau_dev = out["tau"][:sample].cpu().numpy()
+            tau_dev = tau_first[:sample]
             ok = (r["status"] == 1) & (status[:sample] == 1)
             err = np.abs(tau_dev[ok] - r["tau"][ok]).max(1) / np.maximum(1.0, np.abs(r["tau"][ok]).max(1))
             line["cpu_baseline"]["tau_rel_diff_median"] = float(np.median(err)) if err.size else None

@@ -248,6 +248,9 @@ static int reg_tile(int NK) {
   static const int sizes[] = {2, 4, 6, 8, 10, 12, 14, 16};
   for (int c : sizes)
     if (admm_reg_positions(c, 8) >= NK) return c * 100 + 8;
+  // 128 < NK <= 144 (the dense (68, 71) pair of SURVEY.md 8(d)): 16 lanes per row group, 9 columns per thread,
+  // 576 threads, one CTA per SM
+  if (NK <= admm_reg_positions(9, 16)) return 9 * 100 + 16;
   return 0;
 }
 template <int TC, int NB>
@@ -284,6 +287,7 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
                                long long B, cudaStream_t stream) {
   switch (reg_tile(n + mg)) {
     case 516: return launch_reg<5, 16>(st, qb, n, mg, nbx, base, B, stream);
+    case 916: return launch_reg<9, 16>(st, qb, n, mg, nbx, base, B, stream);
     case 1008: return launch_reg<10, 8>(st, qb, n, mg, nbx, base, B, stream);
 #ifndef QPC_ONLY_ATLAS  /* development builds (register-liveness dumps) instantiate the Atlas tiles only */
     case 208: return launch_reg<2, 8>(st, qb, n, mg, nbx, base, B, stream);

@@ -105,7 +105,7 @@ def dense_config(torch, n, m, B, steps, warmup, flush, peak_tf):
     flops = float(W(n, m, K, 1.0 + K / 200.0))  # R is not returned by this entry point: ~1 refactorisation per 200 its
     return dict(n=n, m=m, batch=B, ms=ms, solves_per_s=B / (ms * 1e-3), iters_mean=K,
                 solved_frac=float(np.mean(stt == 1)), tflops_W=flops * B / (ms * 1e-3) / 1e12,
-                frac_of_dfma_peak=flops * B / (ms * 1e-3) / 1e12 / peak_tf, kernel="register tile" if n + m <= 128 else
+                frac_of_dfma_peak=flops * B / (ms * 1e-3) / 1e12 / peak_tf, kernel="register tile" if n + m <= 144 else
                 "shared-memory / global-scratch fallback")
 
 
