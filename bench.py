@@ -108,6 +108,13 @@ class ClockSampler:
         return out
 
 
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def build_workload(batch, rank, settings_name):
     import qpc_loader
     qpc = qpc_loader.load()
@@ -128,14 +135,14 @@ def run_reference(args, rank, world):
     q, v = qpc.scenarios.atlas_random_states(mech, qnom, sample, seed=3)
     oc = orc.OracleController(low.program)
     oc.set_settings(settings, warm_start=0)
-    cores = orc.max_threads()
+    cores = host_cores()  # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on
     for _ in range(args.warmup):
         oc.reset()
-        oc.solve_batch(q, v)
+        oc.solve_batch(q, v, nthreads=cores)
     secs = []
     for _ in range(args.steps):
         oc.reset()
-        r = oc.solve_batch(q, v)
+        r = oc.solve_batch(q, v, nthreads=cores)
         secs.append(r["seconds"])
     total = float(np.sum(secs))
     value = sample * args.steps / total
@@ -377,18 +384,19 @@ def main():
             "accepted_frac": accepted, "iters_max": float(iters.max()), "wall_s_timed_region": wall,
             "sequential_ticks": seq,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             from oracle import oracle as orc
+            ncores = host_cores()
             sample = min(args.cpu_sample, B)
             oc = orc.OracleController(low.program)
             oc.set_settings(settings, warm_start=0)
             kw = {}
             if cm is not None:
                 kw = dict(cweight=cw[:sample], cmaxnf=cm[:sample])
-            oc.solve_batch(q[:64], v[:64])
+            oc.solve_batch(q[:64], v[:64], nthreads=ncores)
             oc.reset()
-            r = oc.solve_batch(q[:sample], v[:sample], **kw)
-            line["cpu_baseline"] = {"value": sample / r["seconds"], "unit": UNIT, "cores": orc.max_threads(),
+            r = oc.solve_batch(q[:sample], v[:sample], nthreads=ncores, **kw)
+            line["cpu_baseline"] = {"value": sample / r["seconds"], "unit": UNIT, "cores": ncores,
                                     "kind": "port", "sample": f"first {sample} instances of rank 0's batch, "
                                     "oracle/ lifted sparse-LDL OSQP restatement, OpenMP over instances, cold start",
                                     "iters_mean": float(r["iters"].mean())}

@@ -88,6 +88,15 @@ typedef struct {
   const double* contact_weight;         /* [B][contact_stride] or NULL = qpc_set_contact_params values */
   const double* contact_maxnormalforce; /* [B][contact_stride] or NULL */
   int64_t contact_stride;   /* >= ncontacts, or 0 to broadcast one row */
+  /* Remaining per-tick Parameters of the reference; both may be NULL (= setup-time values): */
+  const double* task_weight;      /* [B][task_weight_stride] scalar weight of every task in addtask! order -- a
+                                     Parameter-valued `weight` of addtask!(controller, task, weight), momentum.jl:107-110;
+                                     entries of hard and matrix-weighted tasks are ignored */
+  int64_t task_weight_stride;     /* >= ntasks, or 0 to broadcast one row */
+  const double* contact_geometry; /* [B][contact_geometry_stride]: per contact position[3], normal[3] (body frame) and
+                                     mu -- ContactPoint.position / .normal / .mu as Parameters, contacts.jl:39,53-61;
+                                     exercised by test/controller.jl:42-47,110-118 */
+  int64_t contact_geometry_stride; /* >= 7 * ncontacts, or 0 to broadcast one row */
 } qpc_batch_in;
 
 /* Outputs of one batched tick: what the reference leaves in tau (momentum.jl:75-80), controller.result.vd (:62-64)

@@ -234,6 +234,17 @@ void orc_lifted_qp(void* cp, const double* q, const double* v, const double* des
 // Batched control tick: `Threads.@threads over instances`, one private workspace per thread.
 // Strides of 0 for desired/cweight/cmaxnf broadcast one row to every instance; null pointers use the defaults.
 // Returns wall seconds spent in the parallel region.
+// per-tick Parameters beyond desireds / contact weight / maxnormalforce: task weights [B][ntasks] and contact geometry
+// [B][ncontacts][7] (position, normal, mu), both optional; used by orc_solve_batch when set (test infrastructure)
+static const double* g_tweight = nullptr;
+static const double* g_cgeom = nullptr;
+static int64_t g_tweight_stride = 0, g_cgeom_stride = 0;
+void orc_set_tick_parameters(const double* tweight, int64_t tweight_stride, const double* cgeom, int64_t cgeom_stride) {
+  g_tweight = tweight;
+  g_tweight_stride = tweight_stride;
+  g_cgeom = cgeom;
+  g_cgeom_stride = cgeom_stride;
+}
 double orc_solve_batch(void* cp, int64_t B, const double* q, const double* v, const double* desired,
                        int64_t desired_stride, const double* cweight, const double* cmaxnf, int64_t contact_stride,
                        double* tau, double* vd, double* wrenches, int32_t* status, int32_t* iters, double* res,
@@ -252,7 +263,8 @@ double orc_solve_batch(void* cp, int64_t B, const double* q, const double* v, co
     Controller::Result r = k.tick(
         w, q + i * m.nq, v + i * m.nv, desired ? desired + i * desired_stride : nullptr,
         cweight ? cweight + i * contact_stride : nullptr, cmaxnf ? cmaxnf + i * contact_stride : nullptr,
-        tau + i * m.nv, vd + i * m.nv, wrenches ? wrenches + i * nc * 6 : nullptr, xlift ? xlift + i * k.nvar : nullptr);
+        tau + i * m.nv, vd + i * m.nv, wrenches ? wrenches + i * nc * 6 : nullptr, xlift ? xlift + i * k.nvar : nullptr,
+        g_tweight ? g_tweight + i * g_tweight_stride : nullptr, g_cgeom ? g_cgeom + i * g_cgeom_stride : nullptr);
     status[i] = r.status;
     if (iters) iters[i] = r.iter;
     if (rho_updates) rho_updates[i] = r.rho_updates;

@@ -283,7 +283,10 @@ class Controller {
   }
 
   // Evaluate every parameter for the current state and write the lifted QP values.
-  void assemble(Workspace& w, const double* desired, const double* cweight, const double* cmaxnf) const {
+  // tweight: per-tick scalar weights, one per task in addtask! order (Parameter weights, momentum.jl:107-110), or null;
+  // cgeom: per-tick contact position[3], normal[3], mu per contact (Parameters of contacts.jl:39,53-61), or null
+  void assemble(Workspace& w, const double* desired, const double* cweight, const double* cmaxnf,
+                const double* tweight = nullptr, const double* cgeom = nullptr) const {
     const Mechanism& m = *mech;
     const State& s = w.state;
     const int nv = m.nv;
@@ -302,7 +305,13 @@ class Controller {
     size_t ci = 0;
     for (auto& ev : events) {
       if (ev.first == 0) {
-        const Contact& c = contacts[ev.second];
+        Contact c = contacts[ev.second];
+        if (cgeom) {
+          const double* gq = cgeom + 7 * ev.second;
+          c.pos = V3{gq[0], gq[1], gq[2]};
+          c.normal = V3{gq[3], gq[4], gq[5]};
+          c.mu = gq[6];
+        }
         int row = c_row0[ci++];
         forcebasis(c.mu, N, B.data());
         double maxrho = cmaxnf[ev.second] / (N * std::sqrt(c.mu * c.mu + 1));  // contacts.jl:57
@@ -382,9 +391,10 @@ class Controller {
     for (int j = 0; j < nv; j++) pv.push_back(2 * reg[j]);
     for (size_t cc = 0; cc < contacts.size(); cc++)
       for (int k = 0; k < 3; k++) pv.push_back(2 * cweight[cc]);
-    for (auto& t : tasks) {
+    for (size_t ti = 0; ti < tasks.size(); ti++) {
+      const Task& t = tasks[ti];
       if (t.mode == M_SCALAR)
-        for (int k = 0; k < t.dim; k++) pv.push_back(2 * t.weight);
+        for (int k = 0; k < t.dim; k++) pv.push_back(2 * (tweight ? tweight[ti] : t.weight));
       if (t.mode == M_MATRIX)
         for (int c = 0; c < t.dim; c++)
           for (int r = 0; r <= c; r++) pv.push_back(t.W[r * t.dim + c] + t.W[c * t.dim + r]);
@@ -401,7 +411,7 @@ class Controller {
   // (controller::MomentumBasedController)(tau, t, x)  momentum.jl:41-81, preceded (if enabled) by standing.jl:58-85
   Result tick(Workspace& w, const double* q, const double* v, const double* desired_in, const double* cweight,
               const double* cmaxnf, double* tau, double* vd, double* wrenches /*ncontacts x 6 world*/,
-              double* xlift /*nvar or null*/) const {
+              double* xlift /*nvar or null*/, const double* tweight = nullptr, const double* cgeom = nullptr) const {
     const Mechanism& m = *mech;
     update_state(m, q, v, w.state);
     w.des.assign(ndes, 0.0);
@@ -409,7 +419,7 @@ class Controller {
     if (standing.enabled) standing_desireds(w.state, w.des.data());
     if (!cweight) cweight = default_weight.data();
     if (!cmaxnf) cmaxnf = default_maxnf.data();
-    assemble(w, w.des.data(), cweight, cmaxnf);
+    assemble(w, w.des.data(), cweight, cmaxnf, tweight, cgeom);
     if (!w.ready) {
       Csc P = Ppat, A = Apat;
       P.x = w.Px;

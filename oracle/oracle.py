@@ -217,9 +217,12 @@ class OracleController:
                             _d(u))
         return P, qq, A, l, u
 
-    def solve_batch(self, q, v, desired=None, cweight=None, cmaxnf=None, nthreads=0, return_lifted=False):
+    def solve_batch(self, q, v, desired=None, cweight=None, cmaxnf=None, nthreads=0, return_lifted=False,
+                    task_weight=None, contact_geometry=None):
         """Batched tick.  q [B,nq], v [B,nv]; desired [B,ndes] / [ndes] / None (task defaults); contact arrays
-        [B,nc] / [nc] / None (ContactPoint values)."""
+        [B,nc] / [nc] / None (ContactPoint values); task_weight [B,ntasks] per-tick scalar task weights and
+        contact_geometry [B,nc,7] per-tick (position, normal, mu) -- the reference's Parameter-valued weights and contact
+        frames (momentum.jl:107-110, contacts.jl:39,53-61)."""
         q, v = np.atleast_2d(_c(q)), np.atleast_2d(_c(v))
         B = q.shape[0]
         nv, nc = self.m.nv, self.ncontacts
@@ -241,10 +244,15 @@ class OracleController:
                    status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32), res=np.zeros((B, 2)),
                    rho_updates=np.zeros(B, np.int32))
         xl = np.zeros((B, self.nvar)) if return_lifted else None
+        tw = None if task_weight is None else _c(np.broadcast_to(task_weight, (B, len(self.program.tasks))))
+        cg = None if contact_geometry is None else _c(np.broadcast_to(contact_geometry, (B, nc, 7)))
+        lib().orc_set_tick_parameters(_d(tw), C.c_int64(0 if tw is None else tw.shape[1]), _d(cg),
+                                      C.c_int64(0 if cg is None else nc * 7))
         secs = lib().orc_solve_batch(self.h, C.c_int64(B), _d(q), _d(v), _d(desired), C.c_int64(dstride), _d(cweight),
                                      _d(cmaxnf), C.c_int64(cstride), _d(out["tau"]), _d(out["vd"]),
                                      _d(out["wrenches"]), _i(out["status"]), _i(out["iters"]), _d(out["res"]),
                                      _i(out["rho_updates"]), _d(xl), C.c_int(nthreads))
+        lib().orc_set_tick_parameters(None, C.c_int64(0), None, C.c_int64(0))
         out["seconds"] = secs
         if return_lifted:
             out["x_lifted"] = xl

@@ -44,7 +44,9 @@ class qpc_settings(C.Structure):
 
 class qpc_batch_in(C.Structure):
     _fields_ = [("q", C.c_void_p), ("v", C.c_void_p), ("desired", C.c_void_p), ("desired_stride", C.c_int64),
-                ("contact_weight", C.c_void_p), ("contact_maxnormalforce", C.c_void_p), ("contact_stride", C.c_int64)]
+                ("contact_weight", C.c_void_p), ("contact_maxnormalforce", C.c_void_p), ("contact_stride", C.c_int64),
+                ("task_weight", C.c_void_p), ("task_weight_stride", C.c_int64),
+                ("contact_geometry", C.c_void_p), ("contact_geometry_stride", C.c_int64)]
 
 
 class qpc_batch_out(C.Structure):
@@ -173,8 +175,11 @@ class Handles:
             pass
 
     # ---- argument marshalling shared by every compute entry point ----------------------------------------------
-    def batch_in(self, q, v, desired, cw, cm, ptr=lambda a: a.ctypes.data, keep=None):
-        """Builds a qpc_batch_in from arrays (numpy for host pointers; `ptr` extracts the address)."""
+    def batch_in(self, q, v, desired, cw, cm, ptr=lambda a: a.ctypes.data, keep=None, task_weight=None,
+                 contact_geometry=None):
+        """Builds a qpc_batch_in from arrays (numpy for host pointers; `ptr` extracts the address).  task_weight
+        [B, ntasks] / [ntasks] and contact_geometry [B, ncontacts, 7] / [ncontacts, 7] are the per-tick Parameters of
+        the reference (task weights; contact position, normal, mu)."""
         bi = qpc_batch_in()
         bi.q, bi.v = ptr(q), ptr(v)
         bi.desired = None if desired is None else ptr(desired)
@@ -184,6 +189,12 @@ class Handles:
         bi.contact_weight = None if cw is None else ptr(cw)
         bi.contact_maxnormalforce = None if cm is None else ptr(cm)
         bi.contact_stride = 0 if cw is None or cw.ndim == 1 else cw.shape[1]
+        if task_weight is not None:
+            bi.task_weight = ptr(task_weight)
+            bi.task_weight_stride = 0 if task_weight.ndim == 1 else task_weight.shape[1]
+        if contact_geometry is not None:
+            bi.contact_geometry = ptr(contact_geometry)
+            bi.contact_geometry_stride = 0 if contact_geometry.ndim == 2 else contact_geometry.shape[1] * 7
         return bi
 
 
@@ -206,6 +217,15 @@ def _prep_host_inputs(h: Handles, q, v, desired, cw, cm):
         else:
             cm = np.ascontiguousarray(np.broadcast_to(cm, cw.shape))
     return q, v, desired, cw, cm, B
+
+
+def _prep_tick_parameters(h: Handles, task_weight, contact_geometry):
+    tw, cg = _c(task_weight), _c(contact_geometry)
+    if tw is not None and tw.shape[-1] != len(h.program.tasks):
+        raise ValueError(f"task_weight must have {len(h.program.tasks)} columns (one per task, addtask! order)")
+    if cg is not None and cg.shape[-2:] != (h.ncontacts, 7):
+        raise ValueError(f"contact_geometry must be [..., {h.ncontacts}, 7] (position, normal, mu per contact)")
+    return tw, cg
 
 
 def _alloc_out(h: Handles, B):
@@ -259,14 +279,16 @@ class DeviceController:
     def reset_warm_start(self):
         check(self.lib, self.lib.qpc_reset_warm_start(self.h.ctrl), "qpc_reset_warm_start")
 
-    def step_host(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None):
+    def step_host(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None,
+                  task_weight=None, contact_geometry=None):
         """`nsteps` closed-loop ticks on the device (qpc_step_batch); returns (q, v, result of the last tick)."""
         h = self.h
         h.sync_defaults()
         q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
+        tw, cg = _prep_tick_parameters(h, task_weight, contact_geometry)
         q, v = q.copy(), v.copy()
         res = _alloc_out(h, B)
-        bi, bo = h.batch_in(q, v, desired, cw, cm), _batch_out(res)
+        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg), _batch_out(res)
         check(self.lib, self.lib.qpc_step_batch(h.ctrl, C.c_int64(B), C.c_void_p(q.ctypes.data),
                                                 C.c_void_p(v.ctypes.data), C.byref(bi), C.byref(bo), C.c_double(dt),
                                                 C.c_int32(nsteps), C.c_int32(HOST_PTRS), None), "qpc_step_batch")
@@ -289,13 +311,15 @@ class DeviceController:
                                                 C.byref(bi), C.byref(bo), C.c_double(dt), C.c_int32(nsteps),
                                                 C.c_int32(DEVICE_PTRS), C.c_void_p(stream)), "qpc_step_batch")
 
-    def solve_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None) -> BatchResult:
+    def solve_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None, task_weight=None,
+                   contact_geometry=None) -> BatchResult:
         """Host numpy buffers in, host numpy buffers out (H2D + kernels + D2H inside the call)."""
         h = self.h
         h.sync_defaults()
         q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
+        tw, cg = _prep_tick_parameters(h, task_weight, contact_geometry)
         res = _alloc_out(h, B)
-        bi, bo = h.batch_in(q, v, desired, cw, cm), _batch_out(res)
+        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg), _batch_out(res)
         check(self.lib, self.lib.qpc_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo), C.c_int32(HOST_PTRS),
                                                  None), "qpc_solve_batch")
         return res
@@ -329,15 +353,17 @@ class DeviceController:
         check(self.lib, self.lib.qpc_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo),
                                                  C.c_int32(DEVICE_PTRS), C.c_void_p(stream)), "qpc_solve_batch")
 
-    def assemble_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None):
+    def assemble_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None, task_weight=None,
+                      contact_geometry=None):
         """Stage-level entry point: the condensed QP of every instance."""
         h = self.h
         h.sync_defaults()
         q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
+        tw, cg = _prep_tick_parameters(h, task_weight, contact_geometry)
         out = dict(P=np.zeros((B, h.n, h.n)), q=np.zeros((B, h.n)), G=np.zeros((B, h.mg, h.n)),
                    lg=np.zeros((B, h.mg)), ug=np.zeros((B, h.mg)), lb=np.zeros((B, h.nbox)), ub=np.zeros((B, h.nbox)),
                    desired=np.zeros((B, h.ndes)))
-        bi = h.batch_in(q, v, desired, cw, cm)
+        bi = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg)
         check(self.lib, self.lib.qpc_assemble_batch(h.ctrl, C.c_int64(B), C.byref(bi), _p(out["P"]), _p(out["q"]),
                                                     _p(out["G"]), _p(out["lg"]), _p(out["ug"]), _p(out["lb"]),
                                                     _p(out["ub"]), _p(out["desired"]), C.c_int32(HOST_PTRS), None),

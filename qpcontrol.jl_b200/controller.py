@@ -102,11 +102,13 @@ class MomentumBasedController:
         return self._dev
 
     def __call__(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None,
-                 check: bool = True) -> BatchResult:
+                 check: bool = True, task_weight=None, contact_geometry=None) -> BatchResult:
         """The control tick for B instances.  `desired` [B, ndes] (task order) overrides the tasks' `setdesired!`
-        values; contact arrays [B, ncontacts] override the ContactPoint fields per instance."""
+        values; contact arrays [B, ncontacts] override the ContactPoint fields per instance; `task_weight`
+        [B, ntasks] and `contact_geometry` [B, ncontacts, 7] = (position, normal, mu) are the reference's
+        Parameter-valued task weights and contact frames (momentum.jl:107-110, contacts.jl:39,53-61)."""
         dev = self.finalize()
-        res = dev.solve_host(q, v, desired, contact_weight, contact_maxnormalforce)
+        res = dev.solve_host(q, v, desired, contact_weight, contact_maxnormalforce, task_weight, contact_geometry)
         if check:
             checkstatus(res.status)
         return res

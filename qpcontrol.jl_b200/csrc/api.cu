@@ -14,10 +14,10 @@ struct DeviceBuffers {
   double *des = nullptr, *x = nullptr, *y = nullptr;
   double* rho = nullptr;  // [capB] rho every slot ended its last accepted solve with (<= 0: none) -- warm start
   // staging for QPC_HOST_PTRS
-  double *q = nullptr, *v = nullptr, *desired = nullptr, *cw = nullptr, *cm = nullptr;
+  double *q = nullptr, *v = nullptr, *desired = nullptr, *cw = nullptr, *cm = nullptr, *tw = nullptr, *cg = nullptr;
   double *tau = nullptr, *vdot = nullptr, *wrench = nullptr, *res = nullptr;
   int *status = nullptr, *iters = nullptr;
-  long long capB = 0, cap_desired = 0, cap_contact = 0;
+  long long capB = 0, cap_desired = 0, cap_contact = 0, cap_tw = 0, cap_cg = 0;
 };
 struct Backend {
   bool dirty = false;
@@ -183,7 +183,8 @@ static cudaError_t grow(T*& p, long long count) {
   return cudaMalloc((void**)&p, sizeof(T) * (size_t)(count > 0 ? count : 1));
 }
 
-static int ensure_capacity(qpc_controller* c, long long B, long long dstride, long long cstride) {
+static int ensure_capacity(qpc_controller* c, long long B, long long dstride, long long cstride, long long twstride = 0,
+                           long long cgstride = 0) {
   DeviceBuffers& b = c->be.buf;
   const DevProgram& p = c->prog;
   if (B > b.capB) {
@@ -212,6 +213,16 @@ static int ensure_capacity(qpc_controller* c, long long B, long long dstride, lo
     b.capB = B;
     b.cap_desired = 0;
     b.cap_contact = 0;
+    b.cap_tw = 0;
+    b.cap_cg = 0;
+  }
+  if (B * twstride > b.cap_tw) {
+    CUDA_TRY(grow(b.tw, B * twstride));
+    b.cap_tw = B * twstride;
+  }
+  if (B * cgstride > b.cap_cg) {
+    CUDA_TRY(grow(b.cg, B * cgstride));
+    b.cap_cg = B * cgstride;
   }
   if (B * dstride > b.cap_desired) {
     CUDA_TRY(grow(b.desired, B * dstride));
@@ -362,6 +373,7 @@ struct HostXfer {
   const qpc_batch_in* in;
   const qpc_batch_out* out;
   long long dstride, cstride;  // 0 = one broadcast row (copied once, before the fork)
+  long long twstride = 0, cgstride = 0;
 };
 
 // the tick on device pointers; asynchronous on `stream`
@@ -394,6 +406,12 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
         CUDA_TRY(cudaMemcpyAsync(hb.cm + lo * hx->cstride, hx->in->contact_maxnormalforce + lo * hx->cstride,
                                  sizeof(double) * cnt * hx->cstride, cudaMemcpyHostToDevice, s));
       }
+      if (hx->in->task_weight && hx->twstride)
+        CUDA_TRY(cudaMemcpyAsync(hb.tw + lo * hx->twstride, hx->in->task_weight + lo * hx->twstride,
+                                 sizeof(double) * cnt * hx->twstride, cudaMemcpyHostToDevice, s));
+      if (hx->in->contact_geometry && hx->cgstride)
+        CUDA_TRY(cudaMemcpyAsync(hb.cg + lo * hx->cgstride, hx->in->contact_geometry + lo * hx->cgstride,
+                                 sizeof(double) * cnt * hx->cgstride, cudaMemcpyHostToDevice, s));
     }
     if (timed) cudaEventRecord(c->be.ev[0], s);
     qpc_assemble_kernel<<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
@@ -479,7 +497,7 @@ void qpc_controller_destroy(qpc_controller* c) {
     cudaSetDevice(c->be.device);
     DeviceBuffers& b = c->be.buf;
     void* ptrs[] = {b.P, b.qv, b.G, b.lg, b.ug, b.lb, b.ub, b.des, b.x, b.y, b.q, b.v, b.desired, b.cw,
-                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho};
+                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.tw, b.cg};
     for (int i = 0; i < 4; i++)
       if (c->be.ev[i]) cudaEventDestroy(c->be.ev[i]);
     for (void* p : ptrs)
@@ -503,6 +521,45 @@ int qpc_reserve(qpc_controller* c, int64_t B) {
 
 int64_t qpc_launch_count(const qpc_controller* c) { return c ? (int64_t)c->be.launches.load() : 0; }
 
+// validation of the optional per-tick Parameter arrays (task weights, contact geometry)
+static int check_tick_parameters(const DevProgram& p, const qpc_batch_in* in) {
+  if (!in) return QPC_OK;
+  if (in->task_weight && in->task_weight_stride != 0 && in->task_weight_stride < p.ntasks)
+    return qpc_fail(QPC_ERR_ARG, "task_weight_stride smaller than the number of tasks");
+  if (in->contact_geometry && in->contact_geometry_stride != 0 && in->contact_geometry_stride < 7 * p.ncontacts)
+    return qpc_fail(QPC_ERR_ARG, "contact_geometry_stride smaller than 7 x the number of contacts");
+  return QPC_OK;
+}
+// device pointers: use the caller's arrays; host pointers: broadcast rows are copied here, per-instance rows by the
+// chunk that owns them (HostXfer) or, for qpc_step_batch, as one copy
+static int stage_tick_parameters(qpc_controller* c, long long B, const qpc_batch_in* in, bool host, bool copy_all,
+                                 BatchIO& io, cudaStream_t s) {
+  const DevProgram& p = c->prog;
+  DeviceBuffers& b = c->be.buf;
+  io.tweight = io.cgeom = nullptr;
+  io.tweight_stride = io.cgeom_stride = 0;
+  if (!in) return QPC_OK;
+  if (in->task_weight) {
+    io.tweight_stride = in->task_weight_stride;
+    io.tweight = in->task_weight;
+    if (host) {
+      const long long cnt = io.tweight_stride ? (copy_all ? B * io.tweight_stride : 0) : p.ntasks;
+      if (cnt) CUDA_TRY(cudaMemcpyAsync(b.tw, in->task_weight, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, s));
+      io.tweight = b.tw;
+    }
+  }
+  if (in->contact_geometry) {
+    io.cgeom_stride = in->contact_geometry_stride;
+    io.cgeom = in->contact_geometry;
+    if (host) {
+      const long long cnt = io.cgeom_stride ? (copy_all ? B * io.cgeom_stride : 0) : 7 * p.ncontacts;
+      if (cnt) CUDA_TRY(cudaMemcpyAsync(b.cg, in->contact_geometry, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, s));
+      io.cgeom = b.cg;
+    }
+  }
+  return QPC_OK;
+}
+
 int qpc_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const qpc_batch_out* out, int32_t flags,
                     void* stream_) {
   if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
@@ -523,8 +580,14 @@ int qpc_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const 
   }
   const long long dstride = in->desired ? in->desired_stride : 0, cstride = in->contact_weight ? in->contact_stride : 0;
   const long long drows = dstride ? B : 1, crows = cstride ? B : 1;
-  int rc = ensure_capacity(c, B, in->desired ? (dstride ? dstride : p.ndes) : 0,
-                           in->contact_weight ? (cstride ? cstride : p.ncontacts) : 0);
+  int rc = check_tick_parameters(p, in);
+  if (rc) return rc;
+  const long long twstride = in->task_weight ? in->task_weight_stride : 0;
+  const long long cgstride = in->contact_geometry ? in->contact_geometry_stride : 0;
+  rc = ensure_capacity(c, B, in->desired ? (dstride ? dstride : p.ndes) : 0,
+                       in->contact_weight ? (cstride ? cstride : p.ncontacts) : 0,
+                       in->task_weight ? (twstride ? twstride : p.ntasks) : 0,
+                       in->contact_geometry ? (cgstride ? cgstride : 7 * p.ncontacts) : 0);
   if (rc) return rc;
   DeviceBuffers& b = c->be.buf;
   BatchIO io;
@@ -537,6 +600,8 @@ int qpc_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const 
     io.desired = in->desired;
     io.cweight = in->contact_weight;
     io.cmaxnf = in->contact_maxnormalforce;
+    rc = stage_tick_parameters(c, B, in, false, false, io, stream);
+    if (rc) return rc;
     return run_tick(c, B, io, out->tau, out->vdot, out->wrench, out->status, out->iters, out->residuals,
                     out->factorizations, stream);
   }
@@ -559,7 +624,9 @@ int qpc_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const 
   }
   (void)drows;
   (void)crows;
-  HostXfer hx{in, out, dstride, cstride};
+  rc = stage_tick_parameters(c, B, in, true, false, io, s);
+  if (rc) return rc;
+  HostXfer hx{in, out, dstride, cstride, twstride, cgstride};
   rc = run_tick(c, B, io, b.tau, b.vdot, b.wrench, b.status, b.iters, b.res, nullptr, s, &hx);
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -647,7 +714,12 @@ int qpc_step_batch(qpc_controller* c, int64_t B, double* q, double* v, const qpc
     int rc = upload_program(c);
     if (rc) return rc;
   }
-  int rc = ensure_capacity(c, B, desired ? (dstride ? dstride : p.ndes) : 0, cwt ? (cstride ? cstride : p.ncontacts) : 0);
+  int rc = check_tick_parameters(p, in);
+  if (rc) return rc;
+  rc = ensure_capacity(c, B, desired ? (dstride ? dstride : p.ndes) : 0, cwt ? (cstride ? cstride : p.ncontacts) : 0,
+                       in && in->task_weight ? (in->task_weight_stride ? in->task_weight_stride : p.ntasks) : 0,
+                       in && in->contact_geometry
+                           ? (in->contact_geometry_stride ? in->contact_geometry_stride : 7 * p.ncontacts) : 0);
   if (rc) return rc;
   DeviceBuffers& b = c->be.buf;
   const bool host = flags != QPC_DEVICE_PTRS;
@@ -689,6 +761,8 @@ int qpc_step_batch(qpc_controller* c, int64_t B, double* q, double* v, const qpc
   }
   io.q = dq;
   io.v = dv;
+  rc = stage_tick_parameters(c, B, in, host, true, io, s);
+  if (rc) return rc;
   double* vdot = o.vdot ? o.vdot : b.vdot;
   int* status = o.status ? o.status : b.status;
   const DevProgram* dp = (const DevProgram*)c->be.d_prog;
@@ -792,8 +866,13 @@ int qpc_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
     if (rc) return rc;
   }
   const long long dstride = in->desired ? in->desired_stride : 0, cstride = in->contact_weight ? in->contact_stride : 0;
-  int rc = ensure_capacity(c, B, in->desired ? (dstride ? dstride : p.ndes) : 0,
-                           in->contact_weight ? (cstride ? cstride : p.ncontacts) : 0);
+  int rc = check_tick_parameters(p, in);
+  if (rc) return rc;
+  rc = ensure_capacity(c, B, in->desired ? (dstride ? dstride : p.ndes) : 0,
+                       in->contact_weight ? (cstride ? cstride : p.ncontacts) : 0,
+                       in->task_weight ? (in->task_weight_stride ? in->task_weight_stride : p.ntasks) : 0,
+                       in->contact_geometry
+                           ? (in->contact_geometry_stride ? in->contact_geometry_stride : 7 * p.ncontacts) : 0);
   if (rc) return rc;
   DeviceBuffers& b = c->be.buf;
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
@@ -808,6 +887,8 @@ int qpc_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
     io.desired = in->desired;
     io.cweight = in->contact_weight;
     io.cmaxnf = in->contact_maxnormalforce;
+    rc = stage_tick_parameters(c, B, in, false, false, io, s);
+    if (rc) return rc;
     QpBuffers qb = qp_view(b);
     qb.P = P;
     qb.qv = qv;
@@ -841,6 +922,8 @@ int qpc_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
     io.cweight = b.cw;
     io.cmaxnf = b.cm;
   }
+  rc = stage_tick_parameters(c, B, in, true, true, io, s);
+  if (rc) return rc;
   qpc_assemble_kernel<<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qp_view(b), 0, B);
   c->be.launches += 1;
   CUDA_TRY(cudaGetLastError());

@@ -20,12 +20,15 @@ struct KinSmem {
   double *A;                            // 6 x nv world-frame momentum matrix
   double *GC;                           // ncontacts * N * 6 world wrench of each unit generator
   double *Jt, *bt;                      // 6 x nv task Jacobian scratch, 16 scalars
+  double *tw;                           // QPC_MAXT scalar task weights of this tick
+  double *ct;                           // per contact (kin_ct_stride): z_up rotation 9, position 3, B 3N, B'B N^2, maxrho factor
 };
+QPC_HD int kin_ct_stride(int N) { return 13 + 3 * N + N * N; }
 
 QPC_HD int kin_smem_doubles(int nb, int nq, int nv, int ndes, int nc, int N) {
   const int na = nv > nc ? nv : nc;
   return nq + nv + ndes + 2 * nc + nb * (12 + 6 + 6 + 10 + 10) + nv * 6 + nb * 12 + 24 + 6 * na + nc * N * 6 + 6 * nv +
-         16 + 8;
+         16 + 8 + QPC_MAXT + nc * (13 + 3 * N + N * N);
 }
 QPC_HD KinSmem kin_layout(double* b, int nb, int nq, int nv, int ndes, int nc, int N) {
   KinSmem s;
@@ -46,6 +49,8 @@ QPC_HD KinSmem kin_layout(double* b, int nb, int nq, int nv, int ndes, int nc, i
   s.GC = b;     b += nc * N * 6;
   s.Jt = b;     b += 6 * nv;
   s.bt = b;     b += 16;
+  s.tw = b;     b += QPC_MAXT;
+  s.ct = b;     b += nc * (13 + 3 * N + N * N);
   return s;
 }
 
@@ -63,6 +68,39 @@ QPC_DEV void kin_load(const DevProgram* __restrict__ pg, const BatchIO& io, long
   for (int i = t; i < pg->ncontacts; i += nt) {
     s.cw[i] = io.cweight ? io.cweight[inst * io.contact_stride + i] : pg->def_cweight[i];
     s.cm[i] = io.cmaxnf ? io.cmaxnf[inst * io.contact_stride + i] : pg->def_cmaxnf[i];
+  }
+  for (int i = t; i < pg->ntasks; i += nt)
+    s.tw[i] = io.tweight ? io.tweight[inst * io.tweight_stride + i] : pg->tasks[i].weight;
+  // contact table of this tick: the setup-time ContactPoint geometry, or the per-tick Parameters (contacts.jl:53-61)
+  const int N = pg->N, cts = kin_ct_stride(N);
+  for (int c = t; c < pg->ncontacts; c += nt) {
+    const DevContact& dc = pg->contacts[c];
+    double* ct = s.ct + c * cts;
+    if (!io.cgeom) {
+      for (int i = 0; i < 9; i++) ct[i] = dc.Rz[i];
+      for (int i = 0; i < 3; i++) ct[9 + i] = dc.pos[i];
+      for (int i = 0; i < 3 * N; i++) ct[12 + i] = dc.B[i];
+      for (int i = 0; i < N * N; i++) ct[12 + 3 * N + i] = dc.BtB[i];
+      ct[12 + 3 * N + N * N] = dc.maxrho_factor;
+    } else {
+      const double* gq = io.cgeom + inst * io.cgeom_stride + 7 * c;
+      const double mu = gq[6];
+      rot_between_z(ld3(gq + 3), ct);
+      for (int i = 0; i < 3; i++) ct[9 + i] = gq[i];
+      double* B = ct + 12;
+      for (int g = 0; g < N; g++) {  // forcebasis (contacts.jl:16-23)
+        const double th = g * (6.283185307179586476925 / N);
+        const V3 b = mk3(mu * cos(th), mu * sin(th), 1.0);
+        const double inv = 1.0 / sqrt(dot(b, b));
+        B[g] = b.x * inv;
+        B[N + g] = b.y * inv;
+        B[2 * N + g] = b.z * inv;
+      }
+      for (int a = 0; a < N; a++)
+        for (int b = 0; b < N; b++)
+          ct[12 + 3 * N + a * N + b] = B[a] * B[b] + B[N + a] * B[N + b] + B[2 * N + a] * B[2 * N + b];
+      ct[12 + 3 * N + N * N] = 1.0 / (N * sqrt(mu * mu + 1.0));  // contacts.jl:57
+    }
   }
   QPC_SYNC();
 }
@@ -196,11 +234,13 @@ QPC_DEV void kin_contacts(const DevProgram* __restrict__ pg, KinSmem& s) {
   for (int k = QPC_TID; k < pg->ncontacts * N; k += QPC_NT) {
     const int c = k / N, g = k % N;
     const DevContact& dc = pg->contacts[c];
+    const double* ct = s.ct + c * kin_ct_stride(N);
     Xf Z;
-    for (int i = 0; i < 9; i++) Z.R[i] = dc.Rz[i];
-    Z.p = ld3(dc.pos);
+    for (int i = 0; i < 9; i++) Z.R[i] = ct[i];
+    Z.p = ld3(ct + 9);
     Xf T = xf_mul(body_to_root(s, dc.body), Z);
-    V3 f = rot(T.R, mk3(dc.B[g], dc.B[N + g], dc.B[2 * N + g]));
+    const double* B = ct + 12;
+    V3 f = rot(T.R, mk3(B[g], B[N + g], B[2 * N + g]));
     st6(s.GC + 6 * k, mk6(cross(T.p, f), f));
   }
   QPC_SYNC();
@@ -297,12 +337,12 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
   for (int k = t0; k < pg->ncontacts * N * N; k += nt) {
     const int c = k / (N * N), a = (k / N) % N, b = k % N;
     const DevContact& dc = pg->contacts[c];
-    P[(dc.col0 + a) * n + dc.col0 + b] = 2.0 * s.cw[c] * dc.BtB[a * N + b];
+    P[(dc.col0 + a) * n + dc.col0 + b] = 2.0 * s.cw[c] * s.ct[c * kin_ct_stride(N) + 12 + 3 * N + a * N + b];
   }
   for (int k = t0; k < pg->ncontacts * N; k += nt) {
     const int c = k / N;
     lb[k] = 0.0;
-    ub[k] = s.cm[c] * pg->contacts[c].maxrho_factor;
+    ub[k] = s.cm[c] * s.ct[c * kin_ct_stride(N) + 12 + 3 * N + N * N];
   }
   QPC_SYNC();
   for (int ti = 0; ti < pg->ntasks; ti++) {
@@ -325,7 +365,7 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
     if (t.mode != 0) {
       for (int k = t0; k < t.dim; k += nt) G[(t.row0 + k) * n + t.scol0 + k] = -1.0;
       if (t.mode == 1) {
-        for (int k = t0; k < t.dim; k += nt) P[(t.scol0 + k) * n + t.scol0 + k] = 2.0 * t.weight;
+        for (int k = t0; k < t.dim; k += nt) P[(t.scol0 + k) * n + t.scol0 + k] = 2.0 * s.tw[ti];
       } else {  // e'We with a possibly unsymmetric W: the Hessian is W + W'
         const double* W = pg->Wbuf + t.w_off;
         for (int k = t0; k < t.dim * t.dim; k += nt) {

@@ -206,6 +206,32 @@ QPC_HD void quat_to_rot(double w, double x, double y, double z, double* R) {
   R[7] = 2 * (y * z + w * x);
   R[8] = 1 - 2 * (x * x + y * y);
 }
+// Rotations.rotation_between((0,0,1), v)  (reference src/contacts.jl:11): Rodrigues with sin / cos taken from the cross
+// and dot products directly.  Same result as host_program.h: rotation_between_z up to rounding.
+QPC_HD void rot_between_z(V3 v, double* R) {
+  const double n = sqrt(dot(v, v));
+  const V3 t = (1.0 / n) * v;
+  const double ax = -t.y, ay = t.x;  // (0,0,1) x t
+  const double s = sqrt(ax * ax + ay * ay), c = t.z;
+  for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (s < 1e-14) {
+    if (c < 0) {
+      R[4] = -1;
+      R[8] = -1;
+    }
+    return;
+  }
+  const double kx = ax / s, ky = ay / s, u = 1 - c;
+  R[0] = kx * kx * u + c;
+  R[1] = kx * ky * u;
+  R[2] = ky * s;
+  R[3] = ky * kx * u;
+  R[4] = ky * ky * u + c;
+  R[5] = -kx * s;
+  R[6] = -ky * s;
+  R[7] = kx * s;
+  R[8] = c;
+}
 QPC_HD void axis_angle_to_rot(V3 k, double th, double* R) {
   double s, c;
 #if defined(__CUDA_ARCH__)

@@ -77,6 +77,10 @@ struct DevProgram {
 struct BatchIO {
   const double *q, *v, *desired, *cweight, *cmaxnf;
   long long desired_stride, contact_stride;
+  // per-tick Parameters of the reference beyond the above, both optional:
+  const double* tweight = nullptr;  // [B][tweight_stride] scalar weight of every task, addtask! order (momentum.jl:107-110)
+  const double* cgeom = nullptr;    // [B][cgeom_stride] per contact position[3], normal[3], mu (contacts.jl:39,53-61)
+  long long tweight_stride = 0, cgeom_stride = 0;
 };
 
 // the condensed QP of every instance, as written by the assembly kernel and consumed by the ADMM kernel

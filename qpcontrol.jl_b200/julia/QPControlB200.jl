@@ -214,7 +214,11 @@ end
 struct qpc_batch_in
     q::Ptr{Cdouble}; v::Ptr{Cdouble}; desired::Ptr{Cdouble}; desired_stride::Int64
     contact_weight::Ptr{Cdouble}; contact_maxnormalforce::Ptr{Cdouble}; contact_stride::Int64
+    task_weight::Ptr{Cdouble}; task_weight_stride::Int64            # per-tick Parameter weights (momentum.jl:107-110)
+    contact_geometry::Ptr{Cdouble}; contact_geometry_stride::Int64  # per-tick position / normal / mu (contacts.jl:39)
 end
+qpc_batch_in(q, v, desired, dstride, cw, cm, cstride) =
+    qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, C_NULL, 0, C_NULL, 0)
 struct qpc_batch_out
     tau::Ptr{Cdouble}; vdot::Ptr{Cdouble}; wrench::Ptr{Cdouble}; status::Ptr{Int32}; iters::Ptr{Int32}
     residuals::Ptr{Cdouble}; factorizations::Ptr{Int32}
@@ -223,17 +227,24 @@ end
 # The control tick for B instances: (controller)(tau, t, x) of momentum.jl:41-81 with one COLUMN per instance
 # (Julia is column-major, the C ABI wants [B][n] row-major: a (n x B) Matrix is exactly that memory).
 # tau: nv x B (overwritten), q: nq x B, v: nv x B.  Returns (vdot, wrenches[6, ncontacts, B], status).
+# taskweight (ntasks x B) and contactgeometry (7 x ncontacts x B: position, normal, mu) carry Parameter-valued task
+# weights and contact frames per instance.
 function (c::MomentumBasedController)(tau::Matrix{Float64}, t::Number, q::Matrix{Float64}, v::Matrix{Float64};
                                       maxnormalforce::Union{Nothing,Matrix{Float64}}=nothing,
-                                      weight::Union{Nothing,Matrix{Float64}}=nothing, check::Bool=true)
+                                      weight::Union{Nothing,Matrix{Float64}}=nothing,
+                                      taskweight::Union{Nothing,Matrix{Float64}}=nothing,
+                                      contactgeometry::Union{Nothing,Array{Float64,3}}=nothing, check::Bool=true)
     c.initialized || initialize!(c)
     B = size(q, 2)
     nc = length(c.contacts)
     vdot = similar(v); wrench = zeros(6, nc, B); status = zeros(Int32, B); iters = zeros(Int32, B); res = zeros(2, B)
-    GC.@preserve tau q v vdot wrench status iters res maxnormalforce weight begin
+    GC.@preserve tau q v vdot wrench status iters res maxnormalforce weight taskweight contactgeometry begin
         bin = qpc_batch_in(pointer(q), pointer(v), C_NULL, 0,
                            weight === nothing ? C_NULL : pointer(weight),
-                           maxnormalforce === nothing ? C_NULL : pointer(maxnormalforce), nc)
+                           maxnormalforce === nothing ? C_NULL : pointer(maxnormalforce), nc,
+                           taskweight === nothing ? C_NULL : pointer(taskweight),
+                           taskweight === nothing ? 0 : size(taskweight, 1),
+                           contactgeometry === nothing ? C_NULL : pointer(contactgeometry), 7 * nc)
         bout = qpc_batch_out(pointer(tau), pointer(vdot), pointer(wrench), pointer(status), pointer(iters),
                              pointer(res), C_NULL)
         QPControlB200.check(ccall((:qpc_solve_batch, LIB[]), Cint,

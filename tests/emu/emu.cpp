@@ -37,6 +37,10 @@ static BatchIO make_io(const qpc_batch_in* in) {
   io.cmaxnf = in->contact_maxnormalforce;
   io.desired_stride = in->desired_stride;
   io.contact_stride = in->contact_stride;
+  io.tweight = in->task_weight;
+  io.tweight_stride = in->task_weight_stride;
+  io.cgeom = in->contact_geometry;
+  io.cgeom_stride = in->contact_geometry_stride;
   return io;
 }
 
