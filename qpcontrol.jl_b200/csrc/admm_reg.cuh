@@ -40,7 +40,8 @@ QPC_HD int admm_reg_positions(int TC, int NB) { return NB * TC; }
 QPC_HD int admm_reg_threads(int TC, int NB) { return (NB * TC / REG_TR) * NB; }  // (NP / 4 row groups) x NB blocks
 QPC_HD int admm_reg_smem_doubles(int TC, int NB) {
   const int NP = NB * TC;
-  return REG_TR * TC * admm_reg_threads(TC, NB) + 2 * (2 * NP + 2) + 2 * NP + 3 * REG_MAXW * 16 + 13 * NP + 16;
+  const int NPV = NP + (TC % 4 == 0 ? 2 * NB : 0);  // vectors are padded by 2 per column block when TC % 4 == 0
+  return REG_TR * TC * admm_reg_threads(TC, NB) + 2 * (2 * NPV + 2) + 2 * NPV + 3 * REG_MAXW * 16 + 13 * NP + 16;
 }
 
 #if defined(__CUDACC__)
@@ -161,10 +162,18 @@ struct RegSolver {
   static constexpr int NT = (NP / REG_TR) * NB;    // threads
   static constexpr int LPR = NB / REG_TR;          // lanes that own the same row (they hold identical row state)
   static constexpr int TR = REG_TR;
-  static constexpr int US = NP + 2;           // stride of the double-buffered iteration vectors
-  static constexpr int PS = 2 * NP + 2;       // stride of the double-buffered published pivot rows (same storage)
+  // Position-indexed vectors in shared memory (iteration vectors, published pivot rows, check / scaling vectors) are
+  // read by the NB lanes of a row group at a stride of one column block.  When TC % 4 == 0 that stride is a multiple of
+  // 32 bytes and the 16-byte loads collide (2- to 8-way bank conflicts), so every block is padded by two doubles:
+  // position j lives at VP(j) = j + PAD (j / TC); the stride TC + 2 is conflict-free like the odd multiples of 16 bytes.
+  static constexpr int PAD = (TC % 4 == 0) ? 2 : 0;
+  static constexpr int NPV = NP + PAD * NB;   // padded vector length
+  static constexpr int US = NPV + 2;          // stride of the double-buffered iteration vectors
+  static constexpr int PS = 2 * NPV + 2;      // stride of the double-buffered published pivot rows (same storage)
+  static __device__ __forceinline__ int VP(int j) { return PAD ? j + PAD * (j / TC) : j; }
   // ---- geometry -------------------------------------------------------------------------------------------------
   int n, mg, nbx, NK, tid, q, g, row, h, c0;  // q: column block, g: row group, row: the row this lane owns
+  int cvo, vrow, vg4;  // VP(c0), VP(row), VP(4 g): where this lane's column block / row / row group sit in a vector
   bool isx, isg, hasbox, hasc;  // x-row / general-constraint row / x-row that also owns a box row / owns any row
   // ---- shared memory -----------------------------------------------------------------------------------------------
   double *K0, *uv, *cv, *red, *SC;
@@ -206,7 +215,7 @@ struct RegSolver {
     }
     // the row state is dead weight during the sweep: park it in the (idle) check vector and xprev / yprev slots
     // the row state is per row (both lanes of a pair hold the same values)
-    cv[row] = z;
+    cv[vrow] = z;
     sc(9, row) = yr;
     sc(10, row) = x;
     load_tile();
@@ -224,14 +233,14 @@ struct RegSolver {
     // symmetry, the multiplier of row j), [2 NP] 1 / pivot.
     double* pb = uv;
     auto publish = [&](double* pw, const double (&rowv)[TC], int sm1, bool pivot_lane) {
-      store_vec<TC>(pw + c0, rowv);
+      store_vec<TC>(pw + cvo, rowv);
 #pragma unroll
       for (int c = 0; c < TC; c++) {
         int idx = c + sm1;
         idx -= idx >= TC ? TC : 0;
-        pw[NP + c0 + idx] = rowv[c];
+        pw[NPV + cvo + idx] = rowv[c];
       }
-      if (pivot_lane) pw[2 * NP] = 1.0 / rowv[0];
+      if (pivot_lane) pw[2 * NPV] = 1.0 / rowv[0];
     };
     if (g == 0) publish(pb, a[0], 0, q == 0);
     __syncthreads();
@@ -252,10 +261,10 @@ struct RegSolver {
         }
         const double* pr = pb + (s & 1) * PS;
         const int b = s / TC;  // pivot column block
-        const double dinv = pr[2 * NP];
+        const double dinv = pr[2 * NPV];
         double f[TR];
         {
-          const double2* f2 = reinterpret_cast<const double2*>(pr + NP + 4 * g);
+          const double2* f2 = reinterpret_cast<const double2*>(pr + NPV + vg4);
           const double2 fa = f2[0], fb = f2[1];
           f[0] = fa.x * dinv;
           f[1] = fa.y * dinv;
@@ -267,7 +276,7 @@ struct RegSolver {
 #pragma unroll
         for (int r = 0; r < TR; r++) t0[r] = a[r][0];
         double p[TC];
-        load_vec<TC>(pr + c0, p);
+        load_vec<TC>(pr + cvo, p);
         // a[r][c-1] <- a[r][c] - f[r] p[c]  (the pivot row itself: a[r][c] / pivot)
         // (publishing the next pivot row before the other three rows are updated -- look-ahead -- was measured 5 % slower:
         // it costs the registers that keep the iteration loop spill-free)
@@ -295,7 +304,7 @@ struct RegSolver {
         __syncthreads();
       }
     }
-    z = cv[row];
+    z = cv[vrow];
     yr = sc(9, row);
     x = sc(10, row);
   }
@@ -326,7 +335,7 @@ struct RegSolver {
     for (int r = 0; r < TR; r++) s0[r] = 0.0;
     if constexpr (TC % 2 == 0 && TC >= 6) {
       // software pipeline over 16-byte chunks of the vector, two loads in flight ahead of the DFMAs that consume them
-      const double2* v2 = reinterpret_cast<const double2*>(vec + c0);
+      const double2* v2 = reinterpret_cast<const double2*>(vec + cvo);
       double2 ua = v2[0], ub = v2[1], uc = v2[2];
 #pragma unroll
       for (int k = 0; k < TC / 2; k++) {
@@ -341,7 +350,7 @@ struct RegSolver {
       }
     } else {
       double u[TC];
-      load_vec<TC>(vec + c0, u);
+      load_vec<TC>(vec + cvo, u);
 #pragma unroll
       for (int c = 0; c < TC; c++) {
 #pragma unroll
@@ -374,7 +383,7 @@ struct RegSolver {
     }
     if (isg) rhs = rw;
     else if (hasbox) rhs = fma(cbrho, rw, rhs);
-    if (h == 0) nxt[row] = rhs;
+    if (h == 0) nxt[vrow] = rhs;
   }
 
   // product of the owned row of the scaled, unswept matrix with a vector in shared memory
@@ -384,7 +393,7 @@ struct RegSolver {
     for (int r = 0; r < TR; r++) s0[r] = 0.0;
 #pragma unroll
     for (int c = 0; c < TC; c++) {
-      const double e = v[c0 + c];
+      const double e = v[cvo + c];
 #pragma unroll
       for (int r = 0; r < TR; r++) s0[r] = fma(K0[(r * TC + c) * NT + tid], e, s0[r]);
     }
@@ -401,7 +410,10 @@ struct RegSolver {
     q = tid % NB;
     g = tid / NB;
     c0 = q * TC;
+    cvo = q * (TC + PAD);
     row = 4 * g + ((q / LPR) & 3);
+    vrow = VP(row);
+    vg4 = VP(4 * g);
     h = q % LPR;  // lane 0 of the LPR lanes that own a row does the writing
     NK = n + mg;
     isg = row < mg;
@@ -412,13 +424,13 @@ struct RegSolver {
     K0 = smem;
     uv = K0 + TR * TC * NT;        // 2 x PS (sweep) overlaid by 2 x US (iterations)
     cv = uv + 2 * PS;              // 2 x NP
-    red = cv + 2 * NP;             // 3 x REG_MAXW x 16 (two alternating buffers + the residual check's own)
+    red = cv + 2 * NPV;            // 3 x REG_MAXW x 16 (two alternating buffers + the residual check's own)
     SC = red + 3 * REG_MAXW * 16;  // 13 x NP
     redsel = 0;
     const int m = mg + nbx;
     // ---- load: coalesced global reads, scattered into the thread-major staging area ----------------------------------
     for (int k = tid; k < TR * TC * NT; k += NT) K0[k] = 0.0;
-    for (int k = tid; k < 2 * PS + 2 * NP; k += NT) uv[k] = 0.0;
+    for (int k = tid; k < 2 * PS + 2 * NPV; k += NT) uv[k] = 0.0;
     __syncthreads();
     auto k0_index = [&](int i, int j) {  // element (row position i, column position j)
       const int qq = j / TC;
@@ -461,12 +473,12 @@ struct RegSolver {
     double cscale = 1.0;
     double* sv = cv;  // accumulated scaling of every position, NP entries, written by the row owners
     double S = 1.0;   // accumulated scaling of the owned row (= D for x rows, E for general rows)
-    if (h == 0) sv[row] = 1.0;
+    if (h == 0) sv[vrow] = 1.0;
     __syncthreads();
     unsigned mgm = 0, mxm = 0;  // high words of max_j |a_ij| S_j over constraint columns / x columns, owned row
     auto scaled_maxima = [&]() {
       double dcol[TC];
-      load_vec<TC>(sv + c0, dcol);
+      load_vec<TC>(sv + cvo, dcol);
       unsigned g4[TR], x4[TR];
 #pragma unroll
       for (int r = 0; r < TR; r++) g4[r] = x4[r] = 0u;
@@ -492,7 +504,7 @@ struct RegSolver {
       const double sr = row < NK ? 1.0 / sqrt(limit_scaling(nr)) : 1.0;
       const double eb = hasbox ? 1.0 / sqrt(limit_scaling(fabs(cb))) : 1.0;
       S *= sr;
-      if (h == 0) sv[row] = S;
+      if (h == 0) sv[vrow] = S;
       if (isx) {
         qs *= sr;
         D *= sr;
@@ -518,9 +530,9 @@ struct RegSolver {
     }
     if (st.scaling > 0) {  // apply: a_ij <- S_i S_j a_ij, times c on the P block
       double dcol[TC], srow[TR];
-      load_vec<TC>(sv + c0, dcol);
+      load_vec<TC>(sv + cvo, dcol);
 #pragma unroll
-      for (int r = 0; r < TR; r++) srow[r] = sv[4 * g + r];
+      for (int r = 0; r < TR; r++) srow[r] = sv[vg4 + r];
 #pragma unroll
       for (int c = 0; c < TC; c++) {
         const bool xc = c0 + c >= mg;
@@ -578,7 +590,7 @@ struct RegSolver {
       if (isg) yw = pb_.y0[row] * cscale / E;
       else if (hasbox) yw = pb_.y0[mg + xi - (n - nbx)] * cscale / E;
       yr = yw * sc(5, row);
-      if (h == 0) cv[row] = isx ? x : 0.0;
+      if (h == 0) cv[vrow] = isx ? x : 0.0;
       __syncthreads();
       const double gx = k0_product(cv);
       z = isg ? gx : (hasbox ? cb * x : 0.0);
@@ -593,7 +605,7 @@ struct RegSolver {
       int iter = CI[1];
       if (CI[5]) {
         factor(sigma);
-        if (h == 0) uv[((iter + 1) & 1) * US + row] = rhs_entry(sigma);  // the buffer iteration iter+1 reads
+        if (h == 0) uv[((iter + 1) & 1) * US + vrow] = rhs_entry(sigma);  // the buffer iteration iter+1 reads
         __syncthreads();
       }
       if (iter >= st.max_iter) break;
@@ -627,8 +639,8 @@ struct RegSolver {
       for (int i = 0; i < PARK; i++) park[i] = a[i / TC][i % TC];
       const double y = sc(4, row) * yr;
       if (h == 0) {
-        cv[row] = isx ? x : 0.0;
-        cv[NP + row] = isg ? y : 0.0;
+        cv[vrow] = isx ? x : 0.0;
+        cv[NPV + vrow] = isg ? y : 0.0;
       }
       __syncthreads();
       // ---- residuals ------------------------------------------------------------------------------
@@ -638,7 +650,7 @@ struct RegSolver {
       const double cscale_ = CD[0], cinv = CD[1];
       double rho0 = CD[2];
       double px, py;
-      k0_products(cv, cv + NP, px, py);
+      k0_products(cv, cv + NPV, px, py);
       double* rbuf = red + 2 * (REG_MAXW * 16);
       double pdy = 0.0;  // delta_y projected on the polar of the recession cone (primal infeasibility certificate)
       {
@@ -701,12 +713,12 @@ struct RegSolver {
           if (!prim_ok && ndy > epi && SM(13) < -epi * ndy) {
             // primal infeasibility: |D^-1 A' dy|_inf < eps |E dy|_inf
             if (h == 0) {
-              cv[row] = 0.0;
-              cv[NP + row] = isg ? pdy : 0.0;
+              cv[vrow] = 0.0;
+              cv[NPV + vrow] = isg ? pdy : 0.0;
             }
             __syncthreads();
             double qx, qy;
-            k0_products(cv, cv + NP, qx, qy);
+            k0_products(cv, cv + NPV, qx, qy);
             double na[1];
             na[0] = isx ? fabs((qy + (hasbox ? cbv * pdy : 0.0)) / D_) : 0.0;
             reg_block_reduce<1, 0>(na, red, redsel);
@@ -719,12 +731,12 @@ struct RegSolver {
           if (!dual_ok && ndx > edi && SM(14) < -cscale_ * edi * ndx) {
             // dual infeasibility: |D^-1 P dx|_inf small and A dx inside the recession cone of [l, u]
             if (h == 0) {
-              cv[row] = isx ? dx : 0.0;
-              cv[NP + row] = 0.0;
+              cv[vrow] = isx ? dx : 0.0;
+              cv[NPV + vrow] = 0.0;
             }
             __syncthreads();
             double qx, qy;
-            k0_products(cv, cv + NP, qx, qy);
+            k0_products(cv, cv + NPV, qx, qy);
             double nb2[2];
             nb2[0] = isx ? fabs(qx / D_) : 0.0;
             nb2[1] = 0.0;

@@ -54,9 +54,12 @@ static thread_local std::string g_launch_note;  // resource figures of the last 
   } while (0)
 
 // ---- kernels: one robot instance / one QP per CTA ----------------------------------------------------------------------
-constexpr int ASM_THREADS = 64;
+#ifndef QPC_KIN_THREADS
+#define QPC_KIN_THREADS 64
+#endif
+constexpr int ASM_THREADS = QPC_KIN_THREADS;
 constexpr int ADMM_THREADS = 128;
-constexpr int ID_THREADS = 64;
+constexpr int ID_THREADS = QPC_KIN_THREADS;
 
 __global__ void __launch_bounds__(ASM_THREADS)
 qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb, long long base, long long B) {
