@@ -329,24 +329,26 @@ struct RegSolver {
   // With yr = y/rho the dependent chain after the solve result t is  zt -> zr -> v -> clip -> rhs:
   //   v = zr + yr, z+ = clip(v), yr+ = v - z+, next rhs (general row) = z+ - yr+.
   __device__ __forceinline__ void iterate(const double* __restrict__ vec, double* __restrict__ nxt, double alpha,
-                                          double oma, double sigma) {
+                                          double oma, double sigma, int zf) {
     double s0[TR];
 #pragma unroll
     for (int r = 0; r < TR; r++) s0[r] = 0.0;
     if constexpr (TC % 2 == 0 && TC >= 6) {
-      // software pipeline over 16-byte chunks of the vector, two loads in flight ahead of the DFMAs that consume them
-      const double2* v2 = reinterpret_cast<const double2*>(vec + cvo);
-      double2 ua = v2[0], ub = v2[1], uc = v2[2];
+      // All 16-byte chunks of the vector must be in flight before the first DFMA: ptxas otherwise reuses one register
+      // quad and serialises TC / 2 shared-memory round trips (25 % of the iteration's latency at one CTA per SM, ncu),
+      // whatever the source order or volatility of the loads.  The first element is therefore made to depend on one
+      // word of every later chunk through `zf`, a zero the compiler cannot prove (sign bit of max_iter): three ORs and
+      // an AND on the integer pipe buy back four load latencies.
+      double u[TC];
+      load_vec<TC>(vec + cvo, u);
+      unsigned hx = 0u;
 #pragma unroll
-      for (int k = 0; k < TC / 2; k++) {
-        const double2 un = (k + 3 < TC / 2) ? v2[k + 3] : ua;
+      for (int k = 1; k < TC / 2; k++) hx |= (unsigned)__double2hiint(u[2 * k]);
+      u[0] = __hiloint2double((int)((unsigned)__double2hiint(u[0]) | (hx & (unsigned)zf)), __double2loint(u[0]));
 #pragma unroll
-        for (int r = 0; r < TR; r++) s0[r] = fma(a[r][2 * k], ua.x, s0[r]);
+      for (int c = 0; c < TC; c++) {
 #pragma unroll
-        for (int r = 0; r < TR; r++) s0[r] = fma(a[r][2 * k + 1], ua.y, s0[r]);
-        ua = ub;
-        ub = uc;
-        uc = un;
+        for (int r = 0; r < TR; r++) s0[r] = fma(a[r][c], u[c], s0[r]);
       }
     } else {
       double u[TC];
@@ -598,6 +600,7 @@ struct RegSolver {
     }
     // ---- iterations ------------------------------------------------------------------------------------------------------
     const double alpha = st.alpha, sigma = st.sigma, oma = 1.0 - st.alpha;
+    const int zf = st.max_iter >> 31;  // 0 (max_iter > 0), opaque to the compiler: see iterate()
     constexpr int PARK = QPC_REG_PARK < TR * TC ? QPC_REG_PARK : TR * TC;
     volatile double park[PARK > 0 ? PARK : 1];
     for (;;) {
@@ -617,7 +620,7 @@ struct RegSolver {
         double* un = uv + (iter & 1) * US;
 #pragma unroll 1
         for (int k = next_special - iter - 1; k > 0; k--) {
-          iterate(ub_, un, alpha, oma, sigma);
+          iterate(ub_, un, alpha, oma, sigma, zf);
           __syncthreads();
           const double* tmp = ub_;
           ub_ = un;
@@ -631,7 +634,7 @@ struct RegSolver {
         sc(9, row) = x;
         sc(10, row) = sc(4, row) * yr;
       }
-      iterate(uv + (iter & 1) * US, uv + ((iter + 1) & 1) * US, alpha, oma, sigma);
+      iterate(uv + (iter & 1) * US, uv + ((iter + 1) & 1) * US, alpha, oma, sigma, zf);
       // Manual live-range split: the residual check below never touches the tile but needs ~45 registers of its own;
       // left alone, ptxas spills tile entries for the whole solve and reloads them inside the plain-iteration loop
       // (8 LDL.64 per iteration).  Parking PARK entries in local memory across the check keeps the loop spill-free.

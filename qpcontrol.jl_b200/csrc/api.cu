@@ -271,7 +271,9 @@ template <int TC, int NB>
 static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long base,
                               long long B, cudaStream_t stream) {
   const int NT = admm_reg_threads(TC, NB);
-  const int bytes = admm_reg_smem_doubles(TC, NB) * 8;
+  // QPC_ADMM_SMEM_PAD=<bytes>: development knob, inflates the dynamic shared memory to cap the CTAs per SM
+  static const int pad = [] { const char* e = getenv("QPC_ADMM_SMEM_PAD"); return e ? atoi(e) : 0; }();
+  const int bytes = admm_reg_smem_doubles(TC, NB) * 8 + pad;
   static int configured[64] = {0};  // per device
   int dev = 0;
   cudaGetDevice(&dev);

@@ -12,6 +12,6 @@ tail -c 3000 gpurun_out/${TAG}_bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "ref rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:qpc_admm -s 3 -c 1 -f -o gpurun_out/${TAG}_admm \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --batch 4096 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-tail -5 gpurun_out/${TAG}_pytest_gpu.log gpurun_out/${TAG}_smoke.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:qpc_admm -s 5 -c 1 -f -o gpurun_out/${TAG}_admm \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --batch 65536 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+tail -n 5 gpurun_out/${TAG}_pytest_gpu.log gpurun_out/${TAG}_smoke.log
