@@ -12,4 +12,5 @@ from .program import (ANGULAR, HARD, JOINT, LINEAR, LINEAR_MOMENTUM_RATE, MATRIX
                       OSQPSettings, PointAccelerationTask, Program, QPSolveFailure, SpatialAccelerationTask,
                       checkstatus)
 from .controller import BatchResult, MomentumBasedController, StandingController, center_of_mass_host
+from .urdf import parse_urdf
 from . import scenarios, sharding
