@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="instances per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--masks", action="store_true", help="BASELINE config 4: per-instance active contact sets")
+    ap.add_argument("--as-rank", type=int, default=None, help="development: use the seeds rank R would use (1 GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -199,7 +200,8 @@ def main():
     mech, low, ctrl, qnom = qpc.scenarios.atlas_standing(settings, device=local)
     B = args.batch
     # each rank owns its own block of instances: seed offset = rank (rank 0 = BASELINE config 3's seed 3)
-    q, v = qpc.scenarios.atlas_random_states(mech, qnom, B, seed=3 + 1000 * rank)
+    seed_rank = rank if args.as_rank is None else args.as_rank
+    q, v = qpc.scenarios.atlas_random_states(mech, qnom, B, seed=3 + 1000 * seed_rank)
     cw = cm = None
     if args.masks:
         cm = qpc.scenarios.contact_masks(B, len(low.program.contacts), seed=4 + 1000 * rank)
@@ -269,6 +271,21 @@ def main():
     nfac = out["factorizations"].cpu().numpy().astype(np.float64)
     accepted = float(np.mean((status == 1) | (status == 2)))
     tau_first = out["tau"][:min(args.cpu_sample, B)].cpu().numpy()  # compared with the CPU arm below
+
+    # ---- per-batch latency of smaller batches (BASELINE metric: "per-batch latency us"), device-resident, rank 0's view ---
+    latency = {}
+    for lb in (1, 64, 444, 4096):
+        if lb > B:
+            continue
+        ms_l = []
+        for _ in range(7):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            dev.solve_device(lb, dq, dv, out, contact_weight=dcw, contact_maxnormalforce=dcm, stream=stream.cuda_stream)
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms_l.append(a.elapsed_time(b))
+        latency[str(lb)] = 1e3 * float(np.median(ms_l[2:]))
 
     # ---- end to end through the host-pointer C-ABI call ("e2e") ---------------------------------------------------------
     hq = torch.from_numpy(q).pin_memory()
@@ -366,6 +383,7 @@ def main():
                        "qp_dims_solved": {"n": n_x, "m": m_x}, "l2": "flushed between steps (256 MiB memset)",
                        "model": "atlas-topology 36-DoF humanoid, synthetic inertias (qpcontrol_jl_b200.mechanism.atlas_like)"},
             "per_batch_latency_us": 1e3 * ms_total_max / args.steps,
+            "latency_us_by_batch": latency,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s_max / args.steps, "accepted_frac": e2e_ok},
             "gpu_launches": int(launches),

@@ -175,3 +175,22 @@ def test_no_gpu_fallback_is_an_error():
     from qpcontrol_jl_b200 import _lib
     with pytest.raises(RuntimeError):
         _lib.load("/nonexistent/libqpcontrol_b200.so")
+
+
+def test_steady_state_ticks_do_not_allocate():
+    """test/controller.jl:89-90 (`@allocated controller(...) == 0`) restated for the device: once the workspaces exist
+    (first call / qpc_reserve), further ticks of the same or a smaller batch leave the device's free memory untouched."""
+    import torch
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
+    q, v = scenarios.atlas_random_states(mech, qnom, 2048, seed=12)
+    dev = low.finalize()
+    dev.reserve(2048)
+    ctrl(q, v)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for B in (2048, 512, 2048):
+        ctrl(q[:B], v[:B])
+        low.simulate(q[:B], v[:B], 2e-3, 2, check=False)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free1 == free0
