@@ -383,6 +383,7 @@ def main():
                        "qp_dims_solved": {"n": n_x, "m": m_x}, "l2": "flushed between steps (256 MiB memset)",
                        "model": "atlas-topology 36-DoF humanoid, synthetic inertias (qpcontrol_jl_b200.mechanism.atlas_like)"},
             "per_batch_latency_us": 1e3 * ms_total_max / args.steps,
+            "ms_per_step_each": [round(float(x), 3) for x in ms_steps],
             "latency_us_by_batch": latency,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s_max / args.steps, "accepted_frac": e2e_ok},
