@@ -13,4 +13,4 @@ from .program import (ANGULAR, HARD, JOINT, LINEAR, LINEAR_MOMENTUM_RATE, MATRIX
                       checkstatus)
 from .controller import BatchResult, MomentumBasedController, StandingController, center_of_mass_host
 from .urdf import parse_urdf
-from . import scenarios, sharding
+from . import scenarios, sharding, trajectories
