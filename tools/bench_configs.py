@@ -122,6 +122,32 @@ def main():
     steps, warmup = (2, 1) if args.quick else (5, 3)
     result = {"device": torch.cuda.get_device_name(0), "fp64_dfma_peak_tflops": _lib.measure_fp64_peak(0)}
 
+    # ---- config 1: single Atlas instance -- CPU oracle on one thread (cold / warm-started repeat calls, what the
+    # notebook's @benchmark measures, Standing controller.ipynb:149) next to the device latency of a batch of one -----
+    from oracle import oracle as orc
+    st1 = OSQPSettings.standing_notebook()
+    mech, low, ctrl, qnom = scenarios.atlas_standing(st1)
+    q1 = np.tile(qnom, (64, 1))
+    v1 = np.zeros((64, mech.nv))
+    oc = orc.OracleController(low.program)
+    oc.set_settings(st1, warm_start=0)
+    oc.solve_batch(q1[:4], v1[:4], nthreads=1)
+    cold = oc.solve_batch(q1, v1, nthreads=1)
+    oc.set_settings(st1, warm_start=1)
+    oc.reset()
+    oc.solve_batch(q1[:1], v1[:1], nthreads=1)  # first call of the workspace: cold
+    warm = oc.solve_batch(q1, v1, nthreads=1)   # 64 repeat calls on the same state, each warm-started from the last
+    dev = low.finalize()
+    import torch as _t
+    r1 = tick_config(torch, low, q1[:1], v1[:1], None, None, None, 20, 5, flush)
+    result["config1_atlas_single_instance"] = {
+        "cpu_oracle_1_thread_cold_us_per_solve": 1e6 * cold["seconds"] / 64, "cpu_cold_iters": float(cold["iters"].mean()),
+        "cpu_oracle_1_thread_warm_repeat_us_per_solve": 1e6 * warm["seconds"] / 64,
+        "cpu_warm_iters": float(warm["iters"].mean()),
+        "gpu_batch_of_one_latency_us": 1e3 * r1["ms_per_tick"], "gpu_iters": r1["iters_mean"],
+        "note": "nominal notebook state, eps 1e-5; the CPU numbers are the oracle port (Julia/OSQP.jl cannot run here)"}
+    print("config 1", json.dumps(result["config1_atlas_single_instance"]), flush=True)
+
     # ---- config 2 --------------------------------------------------------------------------------------------------
     mech, low, task = scenarios.acrobot_point_task()
     B2 = 65536 if args.quick else 1 << 20
