@@ -91,3 +91,44 @@ def test_recorded_program_matches_reference_structure():
     assert not pr.contacts[0].isenabled()
     with pytest.raises(ValueError):
         low.addtask(pr.tasks[0].task, np.eye(5))
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """qpc_set_warm_start / qpc_reset_warm_start / qpc_step_batch refuse an unfinalized controller and bad arguments;
+    the qpc_batch_in mirror has the header's field order (task_weight / contact_geometry appended)."""
+    lib = _lib.load()
+    mech = scenarios.atlas_like()
+    arrs = [np.ascontiguousarray(a) for a in (mech.parent, mech.jtype, mech.axis, mech.X_R, mech.X_p, mech.mass,
+                                              mech.com, mech.inertia_origin(), mech.gravity)]
+    h = C.c_void_p(lib.qpc_mechanism_create(C.c_int32(mech.nb), *[_lib._p(a) for a in arrs]))
+    c = C.c_void_p(lib.qpc_controller_create(h, C.c_int32(4), C.c_int32(0), None))
+    assert lib.qpc_set_warm_start(c, C.c_int32(1)) < 0 and b"not finalized" in lib.qpc_last_error()
+    assert lib.qpc_reset_warm_start(c) < 0
+    q, v = np.zeros((1, mech.nq)), np.zeros((1, mech.nv))
+    assert lib.qpc_step_batch(c, C.c_int64(1), _lib._p(q), _lib._p(v), None, None, C.c_double(1e-3), C.c_int32(1),
+                              C.c_int32(0), None) < 0
+    assert lib.qpc_step_batch(None, C.c_int64(1), _lib._p(q), _lib._p(v), None, None, C.c_double(1e-3), C.c_int32(1),
+                              C.c_int32(0), None) < 0
+    lib.qpc_controller_destroy(c)
+    lib.qpc_mechanism_destroy(h)
+    names = [f[0] for f in _lib.qpc_batch_in._fields_]
+    text = open(os.path.join(ROOT, "include", "qpcontrol_b200.h")).read()
+    body = text[text.index("typedef struct {", text.index("Inputs of one batched tick")):text.index("} qpc_batch_in;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = re.findall(r"(\w+);", body)
+    assert names == declared
+
+
+def test_host_mirror_rejects_malformed_tick_parameters():
+    mech, low, ctrl, qnom = scenarios.atlas_standing()
+    from qpcontrol_jl_b200._lib import _prep_tick_parameters
+
+    class H:  # the two attributes _prep_tick_parameters reads
+        program = low.program
+        ncontacts = len(low.program.contacts)
+    with pytest.raises(ValueError):
+        _prep_tick_parameters(H, np.zeros(3), None)
+    with pytest.raises(ValueError):
+        _prep_tick_parameters(H, None, np.zeros((8, 6)))
+    tw, cg = _prep_tick_parameters(H, np.ones(len(low.program.tasks)), np.zeros((2, 8, 7)))
+    assert tw.flags.c_contiguous and cg.shape == (2, 8, 7)
