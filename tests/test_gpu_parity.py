@@ -194,3 +194,33 @@ def test_steady_state_ticks_do_not_allocate():
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert free1 == free0
+
+
+def test_chunked_tick_with_every_per_instance_input_matches_small_batches():
+    """B >= 4096 takes the chunked multi-stream path (per-chunk host copies of every per-instance array); its results
+    must equal the same instances solved in small unchunked batches, host and device pointer modes alike."""
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
+    B = 4608
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=16)
+    rng = np.random.default_rng(16)
+    prog = low.program
+    cm = scenarios.contact_masks(B, len(prog.contacts), seed=16)
+    cw = np.full_like(cm, 1e-3) * rng.uniform(0.5, 2.0, cm.shape)
+    tw = np.array([e.weight for e in prog.tasks])[None, :] * rng.uniform(0.5, 2.0, (B, len(prog.tasks)))
+    cg = np.zeros((B, len(prog.contacts), 7))
+    for c, cp in enumerate(prog.contacts):
+        cg[:, c, 0:3] = np.asarray(cp.position) + rng.uniform(-0.01, 0.01, (B, 3))
+        cg[:, c, 3:6] = np.asarray(cp.normal, dtype=np.float64) + rng.uniform(-0.05, 0.05, (B, 3))
+        cg[:, c, 6] = rng.uniform(0.6, 1.0, B)
+    kw = lambda a, b: dict(contact_weight=cw[a:b], contact_maxnormalforce=cm[a:b], task_weight=tw[a:b],  # noqa: E731
+                           contact_geometry=cg[a:b], check=False)
+    whole = ctrl.lowlevel(q, v, **kw(0, B))
+    parts = [ctrl.lowlevel(q[a:a + 1152], v[a:a + 1152], **kw(a, a + 1152)) for a in range(0, B, 1152)]
+    assert np.array_equal(whole.tau, np.concatenate([p.tau for p in parts]))
+    assert np.array_equal(whole.status, np.concatenate([p.status for p in parts]))
+    assert np.array_equal(whole.wrenches, np.concatenate([p.wrenches for p in parts]))
+    # closed loop over the chunked path == closed loop of the parts
+    q1, v1, r1 = low.simulate(q, v, 2e-3, 3, None, cw, cm, check=False)
+    q2 = np.concatenate([low.simulate(q[a:a + 1152], v[a:a + 1152], 2e-3, 3, None, cw[a:a + 1152], cm[a:a + 1152],
+                                      check=False)[0] for a in range(0, B, 1152)])
+    assert np.array_equal(q1, q2)
