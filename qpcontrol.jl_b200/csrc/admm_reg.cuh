@@ -41,7 +41,8 @@ QPC_HD int admm_reg_threads(int TC, int NB) { return (NB * TC / REG_TR) * NB; } 
 QPC_HD int admm_reg_smem_doubles(int TC, int NB) {
   const int NP = NB * TC;
   const int NPV = NP + (TC % 4 == 0 ? 2 * NB : 0);  // vectors are padded by 2 per column block when TC % 4 == 0
-  return REG_TR * TC * admm_reg_threads(TC, NB) + 2 * (2 * NPV + 2) + 2 * NPV + 3 * REG_MAXW * 16 + 13 * NP + 16;
+  // K0 planes are strided by NT + 1 (see RegSolver::KS)
+  return REG_TR * TC * (admm_reg_threads(TC, NB) + 1) + 2 * (2 * NPV + 2) + 2 * NPV + 3 * REG_MAXW * 16 + 13 * NP + 16;
 }
 
 #if defined(__CUDACC__)
@@ -161,6 +162,10 @@ struct RegSolver {
   static constexpr int NP = NB * TC;               // row / column positions: general rows (mg), x rows (n), padding
   static constexpr int NT = (NP / REG_TR) * NB;    // threads
   static constexpr int LPR = NB / REG_TR;          // lanes that own the same row (they hold identical row state)
+  // K0 (the scaled, unswept matrix) is thread-major: plane (r, c) holds entry (r, c) of every thread's tile.  The plane
+  // stride NT + 1 (odd) spreads the scattered 8-byte stores of the load phase (consecutive
+  // matrix columns = consecutive planes) over the banks; with stride NT = 160 they all hit one bank.
+  static constexpr int KS = NT + 1;
   static constexpr int TR = REG_TR;
   // Position-indexed vectors in shared memory (iteration vectors, published pivot rows, check / scaling vectors) are
   // read by the NB lanes of a row group at a stride of one column block.  When TC % 4 == 0 that stride is a multiple of
@@ -197,13 +202,13 @@ struct RegSolver {
 #pragma unroll
     for (int r = 0; r < TR; r++)
 #pragma unroll
-      for (int c = 0; c < TC; c++) a[r][c] = K0[(r * TC + c) * NT + tid];
+      for (int c = 0; c < TC; c++) a[r][c] = K0[(r * TC + c) * KS + tid];
   }
   __device__ __forceinline__ void store_tile() {
 #pragma unroll
     for (int r = 0; r < TR; r++)
 #pragma unroll
-      for (int c = 0; c < TC; c++) K0[(r * TC + c) * NT + tid] = a[r][c];
+      for (int c = 0; c < TC; c++) K0[(r * TC + c) * KS + tid] = a[r][c];
   }
 
   // a <- -(Z^-1) by NP symmetric sweep steps, pivot position s at step s (the -1/rho block first, then the by then
@@ -397,7 +402,7 @@ struct RegSolver {
     for (int c = 0; c < TC; c++) {
       const double e = v[cvo + c];
 #pragma unroll
-      for (int r = 0; r < TR; r++) s0[r] = fma(K0[(r * TC + c) * NT + tid], e, s0[r]);
+      for (int r = 0; r < TR; r++) s0[r] = fma(K0[(r * TC + c) * KS + tid], e, s0[r]);
     }
     return group_reduce<false, NB>(s0, q);
   }
@@ -424,19 +429,19 @@ struct RegSolver {
     hasbox = isx && xi >= n - nbx;
     hasc = hasbox || isg;
     K0 = smem;
-    uv = K0 + TR * TC * NT;        // 2 x PS (sweep) overlaid by 2 x US (iterations)
+    uv = K0 + TR * TC * KS;        // 2 x PS (sweep) overlaid by 2 x US (iterations)
     cv = uv + 2 * PS;              // 2 x NP
     red = cv + 2 * NPV;            // 3 x REG_MAXW x 16 (two alternating buffers + the residual check's own)
     SC = red + 3 * REG_MAXW * 16;  // 13 x NP
     redsel = 0;
     const int m = mg + nbx;
     // ---- load: coalesced global reads, scattered into the thread-major staging area ----------------------------------
-    for (int k = tid; k < TR * TC * NT; k += NT) K0[k] = 0.0;
+    for (int k = tid; k < TR * TC * KS; k += NT) K0[k] = 0.0;
     for (int k = tid; k < 2 * PS + 2 * NPV; k += NT) uv[k] = 0.0;
     __syncthreads();
     auto k0_index = [&](int i, int j) {  // element (row position i, column position j)
       const int qq = j / TC;
-      return ((i & 3) * TC + (j - qq * TC)) * NT + (i >> 2) * NB + qq;
+      return ((i & 3) * TC + (j - qq * TC)) * KS + (i >> 2) * NB + qq;
     };
     for (int k = tid; k < n * n; k += NT) {
       const int i = k / n, j = k - i * n;
