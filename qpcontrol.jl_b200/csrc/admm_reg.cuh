@@ -156,7 +156,7 @@ __device__ __forceinline__ void store_vec(double* __restrict__ p, const double (
   }
 }
 
-template <int TC, int NB>
+template <int TC, int NB, bool ELIM = false>
 struct RegSolver {
   static_assert(NB == 8 || NB == 16, "lanes per row group");
   static constexpr int NP = NB * TC;               // row / column positions: general rows (mg), x rows (n), padding
@@ -177,6 +177,15 @@ struct RegSolver {
   static constexpr int PS = 2 * NPV + 2;      // stride of the double-buffered published pivot rows (same storage)
   static __device__ __forceinline__ int VP(int j) { return PAD ? j + PAD * (j / TC) : j; }
   // ---- geometry -------------------------------------------------------------------------------------------------
+  // ELIM: the leading `nel` variables of the caller's QP have a diagonal, positive cost block and are eliminated from
+  // the KKT system (x_f = -P_ff^-1 (q_f + G_f' nu)): the (g, g) block becomes -(1/rho + M), M = G_f P_ff^-1 G_f', and
+  // the iteration runs on NK = mg + n positions with n the number of KEPT variables.  Requires every general row to be
+  // an equality (then the dual iterate y equals the relaxed average of nu, so x_f = -P_ff^-1 (q_f + G_f' y) is the
+  // primal iterate OSQP would carry with sigma = 0 on those variables).  Ruiz scaling is OSQP's on the FULL problem
+  // (G_f takes part in the row / column norms), residuals are the full problem's.  The floor this form puts on the
+  // primal residual (~1e-7 on Atlas) restricts it to eps_abs >= 1e-6; the host falls back otherwise.
+  int nel = 0, nfull = 0;            // eliminated variables, stride of the caller's P / G / q (= n + nel)
+  double *GF, *PF, *QF, *DF, *UF;    // ELIM: G_f [mg x nel] unscaled, diag P_ff, q_f, column scalings D_f, 1 / diag P_ff
   int n, mg, nbx, NK, tid, q, g, row, h, c0;  // q: column block, g: row group, row: the row this lane owns
   int cvo, vrow, vg4;  // VP(c0), VP(row), VP(4 g): where this lane's column block / row / row group sit in a vector
   bool isx, isg, hasbox, hasc;  // x-row / general-constraint row / x-row that also owns a box row / owns any row
@@ -188,6 +197,8 @@ struct RegSolver {
   // ---- registers: the tile and the state of the owned row -----------------------------------------------------------
   double a[TR][TC];
   double x, z, yr;  // yr = y / rho of the owned constraint row: the iteration never needs y itself
+  double wv;        // ELIM: relaxed average of nu of the owned general row (= the multiplier x_f is built from)
+  double* WV;       // ELIM: wv of every general row, published for the residual products (padded layout)
 
   __device__ __forceinline__ double& sc(int k, int pos) const { return SC[k * NP + pos]; }
 
@@ -371,6 +382,8 @@ struct RegSolver {
     const double rinv = sc(5, row), lo = sc(1, row), up = sc(2, row), cb = sc(3, row), qs = sc(0, row),
                  cbrho = sc(12, row);
     const double w = z - yr, oz = oma * z, ox = oma * x;
+    double ow = 0.0;
+    if constexpr (ELIM) ow = oma * wv;
     const double k1 = alpha * (isg ? rinv : cb);
     const double c1 = (isg ? fma(alpha, w, oz) : oz) + yr;
     asm volatile("" ::"d"(lo), "d"(up), "d"(qs), "d"(cbrho), "d"(k1), "d"(c1), "d"(ox));
@@ -380,6 +393,8 @@ struct RegSolver {
       x = fma(alpha, t, ox);
       rhs = fma(sigma, x, -qs);
     }
+    if constexpr (ELIM)
+      if (isg) wv = fma(alpha, t, ow);  // t = nu on a general row
     if (hasc) {
       const double v = fma(t, k1, c1);
       double zn = v < lo ? lo : v;
@@ -410,6 +425,29 @@ struct RegSolver {
   __device__ __forceinline__ void k0_products(const double* vx, const double* vy, double& px, double& py) const {
     px = k0_product(vx);
     py = k0_product(vy);
+  }
+  // ELIM: as k0_product(vy), but general rows multiply their (g, g) block (-M) with vw instead: x rows get G_k' vy,
+  // general rows -M vw
+  __device__ __forceinline__ double k0_product_yw(const double* vy, const double* vw) const {
+    double s0[TR];
+#pragma unroll
+    for (int r = 0; r < TR; r++) s0[r] = 0.0;
+#pragma unroll
+    for (int c = 0; c < TC; c++) {
+      const double ey = vy[cvo + c], ew = vw[cvo + c];
+#pragma unroll
+      for (int r = 0; r < TR; r++) s0[r] = fma(K0[(r * TC + c) * KS + tid], (4 * g + r < mg) ? ew : ey, s0[r]);
+    }
+    return group_reduce<false, NB>(s0, q);
+  }
+
+  // ELIM: entry tid (< nel) of the scaled G_f' v for a vector of general-row values published at vy (padded layout);
+  // E = sc(6, .) of the general rows
+  __device__ __forceinline__ double gf_transpose_times(const double* vy) const {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < mg; r++) acc = fma(GF[r * nel + tid] * sc(6, r), vy[VP(r)], acc);
+    return acc * DF[tid];
   }
 
   __device__ void solve(const Settings& st, const AdmmProblem& pb_, double* smem) {
@@ -443,22 +481,46 @@ struct RegSolver {
       const int qq = j / TC;
       return ((i & 3) * TC + (j - qq * TC)) * KS + (i >> 2) * NB + qq;
     };
+    if constexpr (!ELIM) {
+      nel = 0;
+      nfull = n;
+    }
     for (int k = tid; k < n * n; k += NT) {
       const int i = k / n, j = k - i * n;
-      K0[k0_index(mg + i, mg + j)] = pb_.P[k];
+      K0[k0_index(mg + i, mg + j)] = pb_.P[(size_t)(nel + i) * nfull + nel + j];
     }
     for (int k = tid; k < mg * n; k += NT) {
       const int r = k / n, j = k - r * n;
-      const double gv = pb_.G[k];
+      const double gv = pb_.G[(size_t)r * nfull + nel + j];
       K0[k0_index(r, mg + j)] = gv;
       K0[k0_index(mg + j, r)] = gv;
+    }
+    if constexpr (ELIM) {
+      GF = SC + 13 * NP + 16;
+      PF = GF + mg * nel;
+      QF = PF + nel;
+      DF = QF + nel;
+      UF = DF + nel;
+      WV = UF + nel;
+      for (int k = tid; k < NPV; k += NT) WV[k] = 0.0;
+      wv = 0.0;
+      for (int k = tid; k < mg * nel; k += NT) {
+        const int r = k / nel, f = k - r * nel;
+        GF[k] = pb_.G[(size_t)r * nfull + f];
+      }
+      for (int f = tid; f < nel; f += NT) {
+        PF[f] = pb_.P[(size_t)f * nfull + f];
+        QF[f] = pb_.qv[f];
+        DF[f] = 1.0;
+        UF[f] = 1.0 / PF[f];
+      }
     }
     x = 0.0;
     z = 0.0;
     yr = 0.0;
     double qs = 0.0, cb = 0.0, l = 0.0, u = 0.0;
     double D = 1.0, E = 1.0;  // accumulated Ruiz scalings of the owned row (E: its constraint row)
-    if (isx) qs = pb_.qv[xi];
+    if (isx) qs = pb_.qv[nel + xi];
     if (isg) {
       l = fmax(pb_.lg[row], -QPC_INFTY);
       u = fmin(pb_.ug[row], QPC_INFTY);
@@ -470,6 +532,33 @@ struct RegSolver {
     }
     __syncthreads();
     load_tile();
+    if constexpr (ELIM) {  // -M (unscaled) into the (g, g) block; the offset G_f P_ff^-1 q_f of the general rows into l, u
+      __syncthreads();  // K0 (the staging copy) has been read by everyone: its head is scratch for M until store_tile()
+      for (int k = tid; k < mg * mg; k += NT) {
+        const int i = k / mg, j = k - i * mg;
+        double acc = 0.0;
+#pragma unroll 1
+        for (int f = 0; f < nel; f++) acc = fma(GF[i * nel + f] * UF[f], GF[j * nel + f], acc);
+        K0[k] = acc;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < TR; r++) {
+        const int i = 4 * g + r;
+#pragma unroll
+        for (int c = 0; c < TC; c++) {
+          const int j = c0 + c;
+          if (i < mg && j < mg) a[r][c] = -K0[i * mg + j];
+        }
+      }
+      if (isg) {
+        double cg = 0.0;
+#pragma unroll 1
+        for (int f = 0; f < nel; f++) cg = fma(GF[row * nel + f] * UF[f], QF[f], cg);
+        l += cg;
+        u += cg;
+      }
+    }
     // ---- Ruiz equilibration of [P A'; A 0]; A = [G; E_box] -----------------------------------------
     // Lazy form: the tile stays unscaled during the `scaling` passes; the accumulated scaling S of every position lives
     // in shared memory and the scaled magnitudes |a_ij| S_j are formed on the fly (one multiply per element and pass;
@@ -483,6 +572,7 @@ struct RegSolver {
     if (h == 0) sv[vrow] = 1.0;
     __syncthreads();
     unsigned mgm = 0, mxm = 0;  // high words of max_j |a_ij| S_j over constraint columns / x columns, owned row
+    double gfm = 0.0, cfm = 0.0;  // ELIM: max_f |G_f[row][f]| D_f (general rows) and max_r |G_f[r][tid]| S_r (tid < nel)
     auto scaled_maxima = [&]() {
       double dcol[TC];
       load_vec<TC>(sv + cvo, dcol);
@@ -501,17 +591,39 @@ struct RegSolver {
       }
       mgm = group_reduce_umax<NB>(g4, q);
       mxm = group_reduce_umax<NB>(x4, q);
+      if constexpr (ELIM) {  // the eliminated columns' share: row maxima of G_f D_f (general rows), column maxima of S G_f
+        gfm = 0.0;
+        if (isg) {
+#pragma unroll 1
+          for (int f = 0; f < nel; f++) gfm = fmax(gfm, fabs(GF[row * nel + f]) * DF[f]);
+        }
+        cfm = 0.0;
+        if (tid < nel) {
+#pragma unroll 1
+          for (int r = 0; r < mg; r++) cfm = fmax(cfm, fabs(GF[r * nel + tid]) * sv[VP(r)]);
+        }
+      }
     };
     if (st.scaling > 0) scaled_maxima();
     __syncthreads();  // every warp has read sv before the first pass overwrites it
     for (int it = 0; it < st.scaling; it++) {
       const double ng = S * __hiloint2double((int)mgm, 0), nx = S * __hiloint2double((int)mxm, 0);
       double nr = isx ? fmax(ng, cscale * nx) : fmax(ng, nx);
+      double dfn = 1.0;  // ELIM: this pass's scaling of eliminated column tid
+      if constexpr (ELIM) {
+        if (isg) nr = fmax(nx, S * gfm);  // the (g, g) block holds -M, which is not part of OSQP's KKT matrix
+        if (tid < nel) {
+          const double d0 = DF[tid];
+          dfn = 1.0 / sqrt(limit_scaling(d0 * fmax(cfm, cscale * d0 * fabs(PF[tid]))));
+        }
+      }
       if (hasbox) nr = fmax(nr, fabs(cb));
       const double sr = row < NK ? 1.0 / sqrt(limit_scaling(nr)) : 1.0;
       const double eb = hasbox ? 1.0 / sqrt(limit_scaling(fabs(cb))) : 1.0;
       S *= sr;
       if (h == 0) sv[vrow] = S;
+      if constexpr (ELIM)
+        if (tid < nel) DF[tid] *= dfn;
       if (isx) {
         qs *= sr;
         D *= sr;
@@ -528,8 +640,14 @@ struct RegSolver {
       double v2[2];
       v2[0] = isx ? fabs(qs) : 0.0;
       v2[1] = (isx && h == 0) ? cscale * S * __hiloint2double((int)mxm, 0) : 0.0;
+      if constexpr (ELIM)
+        if (tid < nel) {  // eliminated columns: |q_bar_f| and the (diagonal) column norm of P_bar_ff
+          const double d1 = DF[tid];
+          v2[0] = fmax(v2[0], cscale * d1 * fabs(QF[tid]));
+          v2[1] += cscale * d1 * d1 * fabs(PF[tid]);
+        }
       reg_block_reduce<1, 1>(v2, red, redsel);
-      double ct = limit_scaling(n > 0 ? v2[1] / n : 1.0);
+      double ct = limit_scaling(n + nel > 0 ? v2[1] / (n + nel) : 1.0);
       const double qn = limit_scaling(v2[0]);
       ct = 1.0 / fmax(ct, qn);
       if (isx) qs *= ct;
@@ -545,7 +663,9 @@ struct RegSolver {
         const bool xc = c0 + c >= mg;
 #pragma unroll
         for (int r = 0; r < TR; r++) {
-          const double f = (xc && 4 * g + r >= mg) ? cscale * srow[r] : srow[r];
+          double f = (xc && 4 * g + r >= mg) ? cscale * srow[r] : srow[r];
+          if constexpr (ELIM)
+            if (!xc && 4 * g + r < mg) f = srow[r] / cscale;  // M_bar = E M E / c
           a[r][c] *= f * dcol[c];
         }
       }
@@ -592,14 +712,22 @@ struct RegSolver {
     }
     __syncthreads();
     if (warm) {  // x_bar = D^-1 x, y_bar = c E^-1 y, z = A x_bar (unprojected, as osqp_warm_start does)
-      if (isx) x = pb_.x0[xi] / D;
+      if (isx) x = pb_.x0[nel + xi] / D;
       double yw = 0.0;
       if (isg) yw = pb_.y0[row] * cscale / E;
       else if (hasbox) yw = pb_.y0[mg + xi - (n - nbx)] * cscale / E;
       yr = yw * sc(5, row);
+      if constexpr (ELIM) wv = isg ? yw : 0.0;
       if (h == 0) cv[vrow] = isx ? x : 0.0;
       __syncthreads();
-      const double gx = k0_product(cv);
+      double gx = k0_product(cv);
+      if constexpr (ELIM)
+        if (isg) {  // + E G_f x_f with the previous tick's x_f (plus the offset that l, u carry)
+          double acc = 0.0;
+#pragma unroll 1
+          for (int f = 0; f < nel; f++) acc = fma(GF[row * nel + f], pb_.x0[f] + QF[f] * UF[f], acc);
+          gx = fma(E, acc, gx);
+        }
       z = isg ? gx : (hasbox ? cb * x : 0.0);
       __syncthreads();
     }
@@ -649,6 +777,7 @@ struct RegSolver {
       if (h == 0) {
         cv[vrow] = isx ? x : 0.0;
         cv[NPV + vrow] = isg ? y : 0.0;
+        if constexpr (ELIM) WV[vrow] = isg ? wv : 0.0;
       }
       __syncthreads();
       // ---- residuals ------------------------------------------------------------------------------
@@ -658,11 +787,18 @@ struct RegSolver {
       const double cscale_ = CD[0], cinv = CD[1];
       double rho0 = CD[2];
       double px, py;
-      k0_products(cv, cv + NPV, px, py);
+      if constexpr (ELIM) {
+        px = k0_product(cv);
+        py = k0_product_yw(cv + NPV, WV);
+      } else {
+        k0_products(cv, cv + NPV, px, py);
+      }
       double* rbuf = red + 2 * (REG_MAXW * 16);
       double pdy = 0.0;  // delta_y projected on the polar of the recession cone (primal infeasibility certificate)
       {
-        const double ax = hasc ? (isg ? px : cbv * x) : 0.0;
+        double ax = hasc ? (isg ? px : cbv * x) : 0.0;
+        if constexpr (ELIM)
+          if (isg) ax = px + py;  // G_k x_k - M w = G x with x_f = -P_ff^-1 (q_f + G_f' w), offset folded into l, u
         const double einv = hasc ? 1.0 / E_ : 0.0;
         const double zz = hasc ? z : 0.0;
         const double r = ax - zz;
@@ -685,10 +821,21 @@ struct RegSolver {
         const double dinv = isx ? 1.0 / D_ : 0.0;
         const double pxx = isx ? px : 0.0, qq = isx ? qs_ : 0.0;
         const double r = pxx + qq + aty;
-        const double big = fmax(fabs(qq), fmax(fabs(aty), fabs(pxx)));
-        red_put<true>(rbuf, 6, fabs(dinv * r));
-        red_put<true>(rbuf, 7, fabs(r));
-        red_put<true>(rbuf, 8, dinv * big);
+        double big = fmax(fabs(qq), fmax(fabs(aty), fabs(pxx))), dbig = dinv * big;
+        double rf = 0.0, drf = 0.0;
+        if constexpr (ELIM)
+          if (tid < nel) {  // eliminated rows: P x_f + q_f = -G_f' w by construction, so the dual residual is G_f' (y - w)
+            const double uy = gf_transpose_times(cv + NPV), uw = gf_transpose_times(WV);
+            const double qf = cscale_ * DF[tid] * QF[tid];
+            const double bf = fmax(fabs(qf), fmax(fabs(uy), fabs(qf + uw)));
+            big = fmax(big, bf);
+            dbig = fmax(dbig, bf / DF[tid]);
+            rf = fabs(uy - uw);
+            drf = rf / DF[tid];
+          }
+        red_put<true>(rbuf, 6, fmax(fabs(dinv * r), drf));
+        red_put<true>(rbuf, 7, fmax(fabs(r), rf));
+        red_put<true>(rbuf, 8, dbig);
         red_put<true>(rbuf, 9, big);
         red_put<true>(rbuf, 10, (isx && !finite_val(x)) ? 1.0 : 0.0);
         red_put<true>(rbuf, 12, isx ? fabs(D_ * dx) : 0.0);
@@ -729,6 +876,8 @@ struct RegSolver {
             k0_products(cv, cv + NPV, qx, qy);
             double na[1];
             na[0] = isx ? fabs((qy + (hasbox ? cbv * pdy : 0.0)) / D_) : 0.0;
+            if constexpr (ELIM)
+              if (tid < nel) na[0] = fmax(na[0], fabs(gf_transpose_times(cv + NPV)) / DF[tid]);
             reg_block_reduce<1, 0>(na, red, redsel);
             if (na[0] < epi * ndy) {
               status = pass ? 3 : -3;
@@ -799,9 +948,14 @@ struct RegSolver {
       __syncthreads();
     }
     // ---- unscale and store -----------------------------------------------------------------------------------------------
+    if constexpr (ELIM) {  // x_f = -P_ff^-1 (q_f + G_f' y) on unscaled quantities (y = E y_bar / c)
+      if (h == 0) WV[vrow] = isg ? wv : 0.0;
+      __syncthreads();
+      if (tid < nel) pb_.x[tid] = -(QF[tid] + gf_transpose_times(WV) * CD[1] / DF[tid]) / PF[tid];
+    }
     if (h == 0) {
       const double cinv = CD[1];
-      if (isx) pb_.x[xi] = sc(6, row) * x;
+      if (isx) pb_.x[nel + xi] = sc(6, row) * x;
       if (pb_.y) {
         const double y = sc(4, row) * yr;
         if (isg) pb_.y[row] = cinv * sc(6, row) * y;

@@ -119,9 +119,10 @@ struct RegTraits {
 #endif
   static constexpr int MAXREG = NB == 16 ? 96 : (TC <= 10 ? QPC_REG_SMALL_TILE : (TC <= 14 ? 255 : 240));
 };
-template <int TC, int NB>
+// ELIM: the leading `nel` variables are eliminated inside the solver (admm_reg.cuh); n stays the caller's dimension
+template <int TC, int NB, bool ELIM = false>
 __global__ void __launch_bounds__((RegTraits<TC, NB>::MAXT)) __maxnreg__((RegTraits<TC, NB>::MAXREG))
-qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long base, long long B) {
+qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long base, long long B, int nel = 0) {
   extern __shared__ double smem[];
   for (long long inst = base + blockIdx.x; inst < B; inst += gridDim.x) {
     AdmmProblem pb;
@@ -143,8 +144,10 @@ qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long
       pb.y0 = pb.y;
       pb.rho_io = qb.rho + inst;
     }
-    RegSolver<TC, NB> s;
-    s.n = n;
+    RegSolver<TC, NB, ELIM> s;
+    s.n = n - (ELIM ? nel : 0);
+    s.nel = ELIM ? nel : 0;
+    s.nfull = n;
     s.mg = mg;
     s.nbx = nbx;
     s.solve(st, pb, smem);
@@ -267,29 +270,29 @@ static int reg_tile(int NK) {
   if (NK <= admm_reg_positions(9, 16)) return 9 * 100 + 16;
   return 0;
 }
-template <int TC, int NB>
+template <int TC, int NB, bool ELIM = false>
 static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long base,
-                              long long B, cudaStream_t stream) {
+                              long long B, cudaStream_t stream, int nel = 0) {
   const int NT = admm_reg_threads(TC, NB);
   // QPC_ADMM_SMEM_PAD=<bytes>: development knob, inflates the dynamic shared memory to cap the CTAs per SM
   static const int pad = [] { const char* e = getenv("QPC_ADMM_SMEM_PAD"); return e ? atoi(e) : 0; }();
-  const int bytes = admm_reg_smem_doubles(TC, NB) * 8 + pad;
-  static int configured[64] = {0};  // per device
+  const int bytes = (admm_reg_smem_doubles(TC, NB) + (ELIM ? mg * nel + 4 * nel + NB * (TC + (TC % 4 == 0 ? 2 : 0)) : 0)) * 8 + pad;
+  static int configured[64] = {0};  // per device (and per instantiation: this is a function template)
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && configured[dev] < bytes) {
-    cudaError_t e = cudaFuncSetAttribute(qpc_admm_reg_kernel<TC, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(qpc_admm_reg_kernel<TC, NB, ELIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(qpc_admm_reg_kernel<TC, NB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(qpc_admm_reg_kernel<TC, NB, ELIM>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured[dev] = bytes;
   }
-  qpc_admm_reg_kernel<TC, NB><<<launch_grid(B - base), NT, bytes, stream>>>(st, qb, n, mg, nbx, base, B);
+  qpc_admm_reg_kernel<TC, NB, ELIM><<<launch_grid(B - base), NT, bytes, stream>>>(st, qb, n, mg, nbx, base, B, nel);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, qpc_admm_reg_kernel<TC, NB>) == cudaSuccess)
+    if (cudaFuncGetAttributes(&fa, qpc_admm_reg_kernel<TC, NB, ELIM>) == cudaSuccess)
       g_launch_note = " [admm_reg TC=" + std::to_string(TC) + " NB=" + std::to_string(NB) + " threads=" +
                       std::to_string(NT) + " regs=" + std::to_string(fa.numRegs) + " dyn_smem=" + std::to_string(bytes) +
                       " static_smem=" + std::to_string(fa.sharedSizeBytes) + " local=" +
@@ -300,7 +303,15 @@ static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, in
 // returns cudaSuccess or the launch error; `smem_configured` = the v1 kernel's attribute was already set for this size
 // instances [base, B)
 static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long base,
-                               long long B, cudaStream_t stream) {
+                               long long B, cudaStream_t stream, int nel = 0) {
+  if (nel > 0) {  // fast path: eliminated free variables, tile chosen for the reduced system (see run_tick for the gate)
+    switch (reg_tile(n - nel + mg)) {
+      case 608: return launch_reg<6, 8, true>(st, qb, n, mg, nbx, base, B, stream, nel);
+      case 808: return launch_reg<8, 8, true>(st, qb, n, mg, nbx, base, B, stream, nel);
+      case 1008: return launch_reg<10, 8, true>(st, qb, n, mg, nbx, base, B, stream, nel);
+      default: break;  // other sizes: the full system below
+    }
+  }
   switch (reg_tile(n + mg)) {
     case 516: return launch_reg<5, 16>(st, qb, n, mg, nbx, base, B, stream);
     case 916: return launch_reg<9, 16>(st, qb, n, mg, nbx, base, B, stream);
@@ -421,8 +432,13 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
     if (timed) cudaEventRecord(c->be.ev[0], s);
     qpc_assemble_kernel<<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
     if (timed) cudaEventRecord(c->be.ev[1], s);
-    if (p.n > 0)
-      CUDA_TRY(launch_admm(p.settings, qb, p.n, p.mg, p.nbx, lo, hi, s));
+    if (p.n > 0) {
+      // Fast path with the diagonal-cost free variables eliminated: only for tolerances above the floor that form puts
+      // on the primal residual, static task weights, and unless QPC_ADMM_ELIM=0
+      static const bool elim_on = [] { const char* e = getenv("QPC_ADMM_ELIM"); return !e || e[0] != '0'; }();
+      const int nel = (elim_on && p.nel > 0 && p.settings.eps_abs >= 1e-6 && !io.tweight) ? p.nel : 0;
+      CUDA_TRY(launch_admm(p.settings, qb, p.n, p.mg, p.nbx, lo, hi, s, nel));
+    }
     else
       qpc_trivial_status_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, s>>>(qb.status, qb.iters, qb.res, lo, hi);
     if (timed) cudaEventRecord(c->be.ev[2], s);

@@ -258,6 +258,15 @@ inline std::string compile_program(const HostController& hc, DevProgram& p) {
     p.def_cweight[c] = hcn.weight;
     p.def_cmaxnf[c] = hcn.maxnf;
   }
+  // fast-path eligibility (admm_reg.cuh, ELIM): every free velocity regularised, every weighted task scalar-weighted
+  // with a positive weight, at least one kept (contact) variable.  All general rows of a controller program are
+  // equalities (hard tasks, slack definitions, wrench balance), which the elimination relies on.
+  p.nel = p.nvf + p.ne;
+  for (int i = 0; i < m.nv; i++)
+    if (p.vcol[i] >= 0 && !(p.reg[i] > 0.0)) p.nel = 0;
+  for (auto& t : hc.tasks)
+    if (t.mode == 2 || (t.mode == 1 && !(t.weight > 0.0))) p.nel = 0;
+  if (p.nbx == 0) p.nel = 0;
   const HostStanding& st = hc.standing;
   p.standing = st.enabled ? 1 : 0;
   if (st.enabled) {

@@ -57,6 +57,8 @@ struct DevProgram {
   int n, nvf, ne, mg, nbx;  // QP the device solves: x = (free vd [nvf], task-error slacks e [ne], rho [nbx]);
                             // mg general (equality) rows, nbx box rows 0 <= rho <= maxrho
   int balance_row0;
+  int nel;  // leading variables of x with a diagonal, strictly positive cost block (regularised free vd, scalar-weight
+            // slacks) that the ADMM fast path may eliminate; 0 when the program does not qualify
   int vcol[QPC_MAXV];      // column of velocity i in x, or -1 when fixed by a hard JointAccelerationTask
   int vfix_des[QPC_MAXV];  // desired offset providing the value of a fixed velocity
   double reg[QPC_MAXV];
