@@ -441,13 +441,27 @@ struct RegSolver {
     return group_reduce<false, NB>(s0, q);
   }
 
-  // ELIM: entry tid (< nel) of the scaled G_f' v for a vector of general-row values published at vy (padded layout);
-  // E = sc(6, .) of the general rows
-  __device__ __forceinline__ double gf_transpose_times(const double* vy) const {
-    double acc = 0.0;
+  // ELIM: the eliminated column fl = tid / 4 is served by the four lanes tid % 4 = 0..3 (requires 4 nel <= NT): entry
+  // fl of the scaled G_f' v for two vectors of general-row values published at vy, vw (padded layout); E = sc(6, .) of
+  // the general rows.  Every lane of the quad returns the complete sums; lanes with fl >= nel return 0.
+  __device__ __forceinline__ void gf_transpose_times2(const double* vy, const double* vw, double& uy, double& uw) const {
+    const int fl = tid >> 2, fp = tid & 3;
+    double ay = 0.0, aw = 0.0;
+    if (fl < nel) {
 #pragma unroll 1
-    for (int r = 0; r < mg; r++) acc = fma(GF[r * nel + tid] * sc(6, r), vy[VP(r)], acc);
-    return acc * DF[tid];
+      for (int r = fp; r < mg; r += 4) {
+        const double gs = GF[r * nel + fl] * sc(6, r);
+        ay = fma(gs, vy[VP(r)], ay);
+        aw = fma(gs, vw[VP(r)], aw);
+      }
+    }
+    ay += __shfl_xor_sync(0xffffffffu, ay, 1);
+    aw += __shfl_xor_sync(0xffffffffu, aw, 1);
+    ay += __shfl_xor_sync(0xffffffffu, ay, 2);
+    aw += __shfl_xor_sync(0xffffffffu, aw, 2);
+    const double d = fl < nel ? DF[fl] : 0.0;
+    uy = ay * d;
+    uw = aw * d;
   }
 
   __device__ void solve(const Settings& st, const AdmmProblem& pb_, double* smem) {
@@ -572,7 +586,8 @@ struct RegSolver {
     if (h == 0) sv[vrow] = 1.0;
     __syncthreads();
     unsigned mgm = 0, mxm = 0;  // high words of max_j |a_ij| S_j over constraint columns / x columns, owned row
-    double gfm = 0.0, cfm = 0.0;  // ELIM: max_f |G_f[row][f]| D_f (general rows) and max_r |G_f[r][tid]| S_r (tid < nel)
+    double gfm = 0.0, cfm = 0.0;  // ELIM: max_f |G_f[row][f]| D_f (general rows) and max_r |G_f[r][fl]| S_r (fl < nel)
+    const int fl = tid >> 2, fp = tid & 3;  // ELIM: eliminated column served by this lane, and its share of the rows
     auto scaled_maxima = [&]() {
       double dcol[TC];
       load_vec<TC>(sv + cvo, dcol);
@@ -593,15 +608,19 @@ struct RegSolver {
       mxm = group_reduce_umax<NB>(x4, q);
       if constexpr (ELIM) {  // the eliminated columns' share: row maxima of G_f D_f (general rows), column maxima of S G_f
         gfm = 0.0;
-        if (isg) {
+        if (isg) {  // the LPR lanes that own the row share the columns
 #pragma unroll 1
-          for (int f = 0; f < nel; f++) gfm = fmax(gfm, fabs(GF[row * nel + f]) * DF[f]);
+          for (int f = h; f < nel; f += LPR) gfm = fmax(gfm, fabs(GF[row * nel + f]) * DF[f]);
         }
+#pragma unroll
+        for (int d = 1; d < LPR; d <<= 1) gfm = fmax(gfm, __shfl_xor_sync(0xffffffffu, gfm, d));
         cfm = 0.0;
-        if (tid < nel) {
+        if (fl < nel) {  // four lanes per eliminated column share the rows
 #pragma unroll 1
-          for (int r = 0; r < mg; r++) cfm = fmax(cfm, fabs(GF[r * nel + tid]) * sv[VP(r)]);
+          for (int r = fp; r < mg; r += 4) cfm = fmax(cfm, fabs(GF[r * nel + fl]) * sv[VP(r)]);
         }
+        cfm = fmax(cfm, __shfl_xor_sync(0xffffffffu, cfm, 1));
+        cfm = fmax(cfm, __shfl_xor_sync(0xffffffffu, cfm, 2));
       }
     };
     if (st.scaling > 0) scaled_maxima();
@@ -612,9 +631,9 @@ struct RegSolver {
       double dfn = 1.0;  // ELIM: this pass's scaling of eliminated column tid
       if constexpr (ELIM) {
         if (isg) nr = fmax(nx, S * gfm);  // the (g, g) block holds -M, which is not part of OSQP's KKT matrix
-        if (tid < nel) {
-          const double d0 = DF[tid];
-          dfn = 1.0 / sqrt(limit_scaling(d0 * fmax(cfm, cscale * d0 * fabs(PF[tid]))));
+        if (fl < nel) {
+          const double d0 = DF[fl];
+          dfn = 1.0 / sqrt(limit_scaling(d0 * fmax(cfm, cscale * d0 * fabs(PF[fl]))));
         }
       }
       if (hasbox) nr = fmax(nr, fabs(cb));
@@ -623,7 +642,7 @@ struct RegSolver {
       S *= sr;
       if (h == 0) sv[vrow] = S;
       if constexpr (ELIM)
-        if (tid < nel) DF[tid] *= dfn;
+        if (fl < nel && fp == 0) DF[fl] *= dfn;
       if (isx) {
         qs *= sr;
         D *= sr;
@@ -641,10 +660,10 @@ struct RegSolver {
       v2[0] = isx ? fabs(qs) : 0.0;
       v2[1] = (isx && h == 0) ? cscale * S * __hiloint2double((int)mxm, 0) : 0.0;
       if constexpr (ELIM)
-        if (tid < nel) {  // eliminated columns: |q_bar_f| and the (diagonal) column norm of P_bar_ff
-          const double d1 = DF[tid];
-          v2[0] = fmax(v2[0], cscale * d1 * fabs(QF[tid]));
-          v2[1] += cscale * d1 * d1 * fabs(PF[tid]);
+        if (fl < nel && fp == 0) {  // eliminated columns: |q_bar_f| and the (diagonal) column norm of P_bar_ff
+          const double d1 = DF[fl];
+          v2[0] = fmax(v2[0], cscale * d1 * fabs(QF[fl]));
+          v2[1] += cscale * d1 * d1 * fabs(PF[fl]);
         }
       reg_block_reduce<1, 1>(v2, red, redsel);
       double ct = limit_scaling(n + nel > 0 ? v2[1] / (n + nel) : 1.0);
@@ -823,16 +842,18 @@ struct RegSolver {
         const double r = pxx + qq + aty;
         double big = fmax(fabs(qq), fmax(fabs(aty), fabs(pxx))), dbig = dinv * big;
         double rf = 0.0, drf = 0.0;
-        if constexpr (ELIM)
-          if (tid < nel) {  // eliminated rows: P x_f + q_f = -G_f' w by construction, so the dual residual is G_f' (y - w)
-            const double uy = gf_transpose_times(cv + NPV), uw = gf_transpose_times(WV);
-            const double qf = cscale_ * DF[tid] * QF[tid];
+        if constexpr (ELIM) {  // eliminated rows: P x_f + q_f = -G_f' w by construction, so the dual residual is G_f' (y - w)
+          double uy, uw;
+          gf_transpose_times2(cv + NPV, WV, uy, uw);
+          if ((tid >> 2) < nel) {
+            const double df = DF[tid >> 2], qf = cscale_ * df * QF[tid >> 2];
             const double bf = fmax(fabs(qf), fmax(fabs(uy), fabs(qf + uw)));
             big = fmax(big, bf);
-            dbig = fmax(dbig, bf / DF[tid]);
+            dbig = fmax(dbig, bf / df);
             rf = fabs(uy - uw);
-            drf = rf / DF[tid];
+            drf = rf / df;
           }
+        }
         red_put<true>(rbuf, 6, fmax(fabs(dinv * r), drf));
         red_put<true>(rbuf, 7, fmax(fabs(r), rf));
         red_put<true>(rbuf, 8, dbig);
@@ -876,8 +897,11 @@ struct RegSolver {
             k0_products(cv, cv + NPV, qx, qy);
             double na[1];
             na[0] = isx ? fabs((qy + (hasbox ? cbv * pdy : 0.0)) / D_) : 0.0;
-            if constexpr (ELIM)
-              if (tid < nel) na[0] = fmax(na[0], fabs(gf_transpose_times(cv + NPV)) / DF[tid]);
+            if constexpr (ELIM) {
+              double uy, uw;
+              gf_transpose_times2(cv + NPV, cv + NPV, uy, uw);
+              if ((tid >> 2) < nel) na[0] = fmax(na[0], fabs(uy) / DF[tid >> 2]);
+            }
             reg_block_reduce<1, 0>(na, red, redsel);
             if (na[0] < epi * ndy) {
               status = pass ? 3 : -3;
@@ -951,7 +975,12 @@ struct RegSolver {
     if constexpr (ELIM) {  // x_f = -P_ff^-1 (q_f + G_f' y) on unscaled quantities (y = E y_bar / c)
       if (h == 0) WV[vrow] = isg ? wv : 0.0;
       __syncthreads();
-      if (tid < nel) pb_.x[tid] = -(QF[tid] + gf_transpose_times(WV) * CD[1] / DF[tid]) / PF[tid];
+      double uy, uw;
+      gf_transpose_times2(WV, WV, uy, uw);
+      if ((tid >> 2) < nel && (tid & 3) == 0) {
+        const int f = tid >> 2;
+        pb_.x[f] = -(QF[f] + uw * CD[1] / DF[f]) / PF[f];
+      }
     }
     if (h == 0) {
       const double cinv = CD[1];

@@ -304,8 +304,11 @@ static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, in
 // instances [base, B)
 static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long base,
                                long long B, cudaStream_t stream, int nel = 0) {
-  if (nel > 0) {  // fast path: eliminated free variables, tile chosen for the reduced system (see run_tick for the gate)
-    switch (reg_tile(n - nel + mg)) {
+  // fast path: eliminated free variables, tile chosen for the reduced system (see run_tick for the gate); four lanes
+  // serve each eliminated column, so 4 nel must not exceed the CTA size
+  const int etile = nel > 0 ? reg_tile(n - nel + mg) : 0;
+  if (etile && 4 * nel <= admm_reg_threads(etile / 100, etile % 100)) {
+    switch (etile) {
       case 608: return launch_reg<6, 8, true>(st, qb, n, mg, nbx, base, B, stream, nel);
       case 808: return launch_reg<8, 8, true>(st, qb, n, mg, nbx, base, B, stream, nel);
       case 1008: return launch_reg<10, 8, true>(st, qb, n, mg, nbx, base, B, stream, nel);
