@@ -163,6 +163,13 @@ int64_t qpc_launch_count(const qpc_controller*);
  * stream; qpc_stage_times waits for the last tick and returns {assembly, ADMM, inverse dynamics} milliseconds */
 int qpc_set_profiling(qpc_controller*, int32_t on);
 int qpc_stage_times(qpc_controller*, double ms[3]);
+/* ADMM fast path: when every free acceleration is regularised and every weighted task has a positive scalar weight
+ * (the StandingController's program, standing.jl:35-49), those variables have a diagonal cost block and every general
+ * row is an equality; the solver then eliminates them from the KKT system (same OSQP iterates, half the flops) as long
+ * as eps_abs >= 1e-6 and no per-tick task weights are passed.  qpc_set_admm_elimination(ctrl, 0) forces the full
+ * system; qpc_admm_eliminated returns how many variables the next tick eliminates (0 = full system). */
+int qpc_set_admm_elimination(qpc_controller*, int32_t on);
+int qpc_admm_eliminated(const qpc_controller*);
 /* fp64 FMA throughput of the device in TFLOP/s (dependent-chain-free DFMA loop), the roofline denominator */
 int qpc_measure_fp64_peak(int32_t device, double* tflops);
 

@@ -60,7 +60,7 @@ SETUP_SYMBOLS = ["qpc_version", "qpc_last_error", "qpc_device_count", "qpc_defau
                  "qpc_standing_setup", "qpc_set_settings", "qpc_finalize", "qpc_controller_dims"]
 COMPUTE_SYMBOLS = ["qpc_solve_batch", "qpc_reserve", "qpc_launch_count", "qpc_assemble_batch", "qpc_solve_qp_batch",
                    "qpc_set_profiling", "qpc_stage_times", "qpc_measure_fp64_peak", "qpc_set_warm_start",
-                   "qpc_reset_warm_start", "qpc_step_batch"]
+                   "qpc_reset_warm_start", "qpc_step_batch", "qpc_set_admm_elimination", "qpc_admm_eliminated"]
 
 _libs = {}
 
@@ -278,6 +278,14 @@ class DeviceController:
 
     def reset_warm_start(self):
         check(self.lib, self.lib.qpc_reset_warm_start(self.h.ctrl), "qpc_reset_warm_start")
+
+    def set_admm_elimination(self, on: bool):
+        """Allow (default) or forbid the ADMM fast path that eliminates the diagonal-cost free variables."""
+        check(self.lib, self.lib.qpc_set_admm_elimination(self.h.ctrl, C.c_int32(int(on))), "qpc_set_admm_elimination")
+
+    def admm_eliminated(self) -> int:
+        """Number of variables the next tick eliminates from the KKT system (0 = full system)."""
+        return int(self.lib.qpc_admm_eliminated(self.h.ctrl))
 
     def step_host(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None,
                   task_weight=None, contact_geometry=None):

@@ -29,6 +29,7 @@ struct Backend {
   std::mutex mu;
   bool profiling = false;
   bool warm_start = false;  // qpc_set_warm_start
+  bool elimination = true;  // qpc_set_admm_elimination: allow the fast path with eliminated free variables
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int* d_nfac = nullptr;  // [capB] factorisations per instance
   // chunked tick: sub-batches go to side streams so that one chunk's assembly / inverse dynamics and the tail of its
@@ -439,7 +440,7 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
       // Fast path with the diagonal-cost free variables eliminated: only for tolerances above the floor that form puts
       // on the primal residual, static task weights, and unless QPC_ADMM_ELIM=0
       static const bool elim_on = [] { const char* e = getenv("QPC_ADMM_ELIM"); return !e || e[0] != '0'; }();
-      const int nel = (elim_on && p.nel > 0 && p.settings.eps_abs >= 1e-6 && !io.tweight) ? p.nel : 0;
+      const int nel = (elim_on && c->be.elimination && p.nel > 0 && p.settings.eps_abs >= 1e-6 && !io.tweight) ? p.nel : 0;
       CUDA_TRY(launch_admm(p.settings, qb, p.n, p.mg, p.nbx, lo, hi, s, nel));
     }
     else
@@ -662,6 +663,22 @@ int qpc_set_warm_start(qpc_controller* c, int32_t on) {
   std::lock_guard<std::mutex> lock(c->be.mu);
   c->be.warm_start = on != 0;
   return QPC_OK;
+}
+
+int qpc_set_admm_elimination(qpc_controller* c, int32_t on) {
+  if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
+  std::lock_guard<std::mutex> lock(c->be.mu);
+  c->be.elimination = on != 0;
+  return QPC_OK;
+}
+
+int qpc_admm_eliminated(const qpc_controller* c) {
+  if (!c || !c->finalized) return 0;
+  const DevProgram& p = c->prog;
+  if (!c->be.elimination || p.nel <= 0 || p.settings.eps_abs < 1e-6) return 0;
+  const int etile = reg_tile(p.n - p.nel + p.mg);
+  return (etile && 4 * p.nel <= admm_reg_threads(etile / 100, etile % 100) &&
+          (etile == 608 || etile == 808 || etile == 1008)) ? p.nel : 0;
 }
 
 int qpc_reset_warm_start(qpc_controller* c) {

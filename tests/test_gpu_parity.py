@@ -224,3 +224,39 @@ def test_chunked_tick_with_every_per_instance_input_matches_small_batches():
     q2 = np.concatenate([low.simulate(q[a:a + 1152], v[a:a + 1152], 2e-3, 3, None, cw[a:a + 1152], cm[a:a + 1152],
                                       check=False)[0] for a in range(0, B, 1152)])
     assert np.array_equal(q1, q2)
+
+
+def test_eliminated_fast_path_reproduces_the_full_system():
+    """ADMM fast path (free variables eliminated from the KKT system) vs the full system on the same batch, notebook
+    settings: the iterates are the same up to rounding -- identical accept/reject, iteration counts equal on almost
+    every instance, torques and wrenches far inside the parity tolerance; with and without warm start."""
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
+    dev = low.finalize()
+    assert dev.admm_eliminated() == 21  # 18 free accelerations + 3 momentum slacks
+    q, v = scenarios.atlas_random_states(mech, qnom, 2048, seed=23)
+    fast = ctrl(q, v, check=False)
+    dev.set_admm_elimination(False)
+    assert dev.admm_eliminated() == 0
+    full = ctrl(q, v, check=False)
+    dev.set_admm_elimination(True)
+    ok = (full.status == 1) | (full.status == 2)
+    assert np.array_equal(ok, (fast.status == 1) | (fast.status == 2))
+    assert np.mean(fast.iters == full.iters) > 0.99 and abs(fast.iters.mean() - full.iters.mean()) < 1.0
+    assert parity.rel_err(fast.tau[ok], full.tau[ok]).max() < 1e-6
+    assert parity.rel_err(fast.wrenches[ok], full.wrenches[ok]).max() < 1e-6
+    assert parity.rel_err(fast.vdot[ok], full.vdot[ok]).max() < 1e-6
+    outs = []
+    for on in (True, False):
+        dev.set_admm_elimination(on)
+        low.set_warm_start(True)
+        low.reset_warm_start()
+        ctrl(q, v, check=False)
+        q2, v2 = q.copy(), v + 2e-3 * fast.vdot
+        outs.append(ctrl(q2, v2, check=False))
+        low.set_warm_start(False)
+    dev.set_admm_elimination(True)
+    assert parity.rel_err(outs[0].tau, outs[1].tau).max() < 1e-5
+    assert abs(outs[0].iters.mean() - outs[1].iters.mean()) < 0.05 * outs[1].iters.mean() + 1.0
+    # tight tolerances stay on the full system
+    mech2, low2, ctrl2, _ = scenarios.atlas_standing(OSQPSettings.test_suite())
+    assert low2.finalize().admm_eliminated() == 0
