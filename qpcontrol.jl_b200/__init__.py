@@ -13,4 +13,5 @@ from .program import (ANGULAR, HARD, JOINT, LINEAR, LINEAR_MOMENTUM_RATE, MATRIX
                       checkstatus)
 from .controller import BatchResult, MomentumBasedController, StandingController, center_of_mass_host
 from .urdf import parse_urdf
-from . import scenarios, sharding, trajectories
+from .se3pd import PDGains, SE3PDController, SE3PDGains
+from . import scenarios, se3pd, sharding, trajectories

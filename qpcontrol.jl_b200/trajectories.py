@@ -3,8 +3,7 @@
 SURVEY.md 8(f) rank 3, first half: the trajectories that feed `setdesired!` / the `desired` batch input.  They are
 evaluated on the host (numpy; `x` may be a scalar or an array of evaluation times, one per robot instance) and their
 outputs go into `qpc_batch_in.desired`.  The second half of rank 3, `SE3PDController` (src/lowlevel/se3pdcontroller.jl),
-adds `pd(::SE3PDGains, ...)` from RigidBodyDynamics.PDControl to `SE3Trajectory`'s feed-forward term; that package is
-absent here, so only the feed-forward part (`SE3Trajectory`) is provided.
+which adds `pd(::SE3PDGains, ...)` to `SE3Trajectory`'s feed-forward term, is in `se3pd.py`.
 
 Call convention mirrors the reference: `traj(x)` returns the value, `traj(x, n)` returns `(value, d/dx, ..., d^n/dx^n)`
 (`Val(n)` in Julia).  Rotations are unit quaternions (w, x, y, z); their derivatives are angular velocity /
