@@ -145,8 +145,10 @@ QPC_DEV void admm_At_times(const AdmmSmem& s, int n, int mg, int nbx, const doub
   for (int base = 0; base < n; base += G) {
     const int j = base + QPC_TID / R;
     double a = 0;
-    if (j < n)
+    if (j < n) {
+      QPC_UNROLL8
       for (int i = sidx; i < mg; i += R) a += s.Gs[i * n + j] * w[i];
+    }
     a = lane_group_sum(a, R);
     if (j < n && sidx == 0) {
       if (j >= n - nbx) a += s.cb[j - (n - nbx)] * w[mg + j - (n - nbx)];
@@ -163,8 +165,10 @@ QPC_DEV void admm_A_times(const AdmmSmem& s, int n, int mg, int nbx, const doubl
   for (int base = 0; base < mg; base += G) {
     const int i = base + QPC_TID / R;
     double a = 0;
-    if (i < mg)
+    if (i < mg) {
+      QPC_UNROLL8
       for (int j = sidx; j < n; j += R) a += s.Gt[j * mg + i] * v[j];
+    }
     a = lane_group_sum(a, R);
     if (i < mg && sidx == 0) out[i] = a;
   }
@@ -178,6 +182,7 @@ QPC_DEV void admm_P_times(const AdmmSmem& s, const double* __restrict__ P, int n
   QPC_SYNC();
   for (int i = QPC_TID; i < n; i += QPC_NT) {
     double a = 0;
+    QPC_UNROLL8
     for (int j = 0; j < n; j++) a += P[j * n + i] * tmp[j];
     out[i] = c * s.D[i] * a;
   }
@@ -209,6 +214,7 @@ QPC_DEV void admm_factor(const AdmmSmem& s, const double* __restrict__ P, int n,
     const int i = k / n, j = k % n;
     if (j > i) continue;
     double a = M[k];
+    QPC_UNROLL8
     for (int r = 0; r < mg; r++) a += s.Gs[r * n + i] * s.rho[r] * s.Gs[r * n + j];
     if (i == j) {
       a += sigma;
@@ -246,6 +252,7 @@ QPC_DEV void admm_factor(const AdmmSmem& s, const double* __restrict__ P, int n,
     QPC_SYNC();
     for (int i = j + 1 + tid; i < n; i += nt) {
       double a = 0;
+      QPC_UNROLL8
       for (int k = j + 1; k <= i; k++) a += M[i * n + k] * col[k];
       M[i * n + j] = -a * dj;
     }
@@ -372,8 +379,10 @@ QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg
     for (int base = 0; base < n; base += Gn) {
       const int i = base + tid / Rn;
       double a = 0;
-      if (i < n)
+      if (i < n) {
+        QPC_UNROLL8
         for (int k = sn; k <= i; k += Rn) a += s.M[k * n + i] * s.rhs[k];
+      }
       a = lane_group_sum(a, Rn);
       if (i < n && sn == 0) s.tv[i] = a;
     }
@@ -382,8 +391,10 @@ QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg
     for (int base = 0; base < n; base += Gn) {
       const int j = base + tid / Rn;
       double a = 0;
-      if (j < n)
+      if (j < n) {
+        QPC_UNROLL8
         for (int i = j + sn; i < n; i += Rn) a += s.M[i * n + j] * s.tv[i];
+      }
       a = lane_group_sum(a, Rn);
       if (j < n && sn == 0) s.xt[j] = a;
     }

@@ -60,6 +60,8 @@ static thread_local std::string g_launch_note;  // resource figures of the last 
 #endif
 constexpr int ASM_THREADS = QPC_KIN_THREADS;
 constexpr int ADMM_THREADS = 128;
+constexpr int ADMM_BIG_THREADS = 512;
+constexpr int ADMM_BIG_SMEM = 100 * 1024;  // above this at most two CTAs fit an SM: run them with ADMM_BIG_THREADS
 constexpr int ID_THREADS = QPC_KIN_THREADS;
 
 __global__ void __launch_bounds__(ASM_THREADS)
@@ -80,7 +82,10 @@ qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb,
   }
 }
 
-__global__ void __launch_bounds__(ADMM_THREADS)
+// NT = ADMM_THREADS for QPs of which several fit one SM's shared memory; ADMM_BIG_THREADS (two CTAs of 16 warps per
+// SM) for the large ones, whose products otherwise leave the SM with 4-8 warps to cover shared-memory / L2 latency
+template <int NT>
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1)
 qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long base, long long B, double* gscratch) {
   extern __shared__ double smem[];
   double* gmat = gscratch ? gscratch + (size_t)blockIdx.x * admm_matrix_doubles(n, mg) : nullptr;
@@ -332,8 +337,14 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
     default: break;
   }
   const int asmem = admm_smem_doubles(n, mg, nbx) * 8;
+  if (asmem <= ADMM_BIG_SMEM) {
+    qpc_admm_kernel<ADMM_THREADS><<<launch_grid(B - base), ADMM_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, base, B, nullptr);
+    return cudaGetLastError();
+  }
   if (asmem <= 227 * 1024) {
-    qpc_admm_kernel<<<launch_grid(B - base), ADMM_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, base, B, nullptr);
+    cudaError_t e = cudaFuncSetAttribute(qpc_admm_kernel<ADMM_BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem);
+    if (e != cudaSuccess) return e;
+    qpc_admm_kernel<ADMM_BIG_THREADS><<<launch_grid(B - base), ADMM_BIG_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, base, B, nullptr);
     return cudaGetLastError();
   }
   // QPs that fit neither the register file nor shared memory: matrices in a per-CTA global scratch (L2 resident for
@@ -347,9 +358,9 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
   double* scratch = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)grid * admm_matrix_doubles(n, mg), stream);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vsmem);
+  e = cudaFuncSetAttribute(qpc_admm_kernel<ADMM_BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsmem);
   if (e == cudaSuccess) {
-    qpc_admm_kernel<<<(int)grid, ADMM_THREADS, vsmem, stream>>>(st, qb, n, mg, nbx, base, B, scratch);
+    qpc_admm_kernel<ADMM_BIG_THREADS><<<(int)grid, ADMM_BIG_THREADS, vsmem, stream>>>(st, qb, n, mg, nbx, base, B, scratch);
     e = cudaGetLastError();
   }
   cudaFreeAsync(scratch, stream);
@@ -362,8 +373,8 @@ static int configure_kernels(const DevProgram& p) {
   if (ksm > 227 * 1024) return qpc_fail(QPC_ERR_LIMIT, "mechanism does not fit the 227 KB shared memory of one CTA");
   CUDA_TRY(cudaFuncSetAttribute(qpc_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
   CUDA_TRY(cudaFuncSetAttribute(qpc_inverse_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
-  if (asmem <= 227 * 1024)
-    CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
+  if (asmem <= ADMM_BIG_SMEM)
+    CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel<ADMM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
   return QPC_OK;
 }
 
@@ -994,8 +1005,8 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
   if (admm_vector_doubles(n, mg, nbox) * 8 > 227 * 1024)
     return qpc_fail(QPC_ERR_LIMIT, "QP vectors do not fit the 227 KB shared memory of one CTA");
   CUDA_TRY(cudaSetDevice(device));
-  if (asmem <= 227 * 1024)
-    CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
+  if (asmem <= ADMM_BIG_SMEM)
+    CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel<ADMM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
   QpBuffers qb;
   memset(&qb, 0, sizeof(qb));
   if (flags == QPC_DEVICE_PTRS) {

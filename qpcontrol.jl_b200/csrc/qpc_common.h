@@ -17,6 +17,7 @@
 #define QPC_NT ((int)blockDim.x)
 #define QPC_SYNC() __syncthreads()
 #define QPC_LDG(p) __ldg(p)
+#define QPC_UNROLL8 _Pragma("unroll 8")  // product loops: eight loads in flight instead of one dependent load per FMA
 #else
 #define QPC_HD inline
 #define QPC_DEV inline
@@ -25,6 +26,7 @@
 #define QPC_NT 1
 #define QPC_SYNC() ((void)0)
 #define QPC_LDG(p) (*(p))
+#define QPC_UNROLL8
 #endif
 
 namespace qpc {

@@ -113,6 +113,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only-dense", action="store_true", help="config 5 only (development: A/B of the large-QP kernels)")
+    ap.add_argument("--dense", default=None, help="n,m,B: one size of config 5 (with --only-dense)")
     args = ap.parse_args()
     import torch
     if not torch.cuda.is_available():
@@ -121,6 +123,13 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     steps, warmup = (2, 1) if args.quick else (5, 3)
     result = {"device": torch.cuda.get_device_name(0), "fp64_dfma_peak_tflops": _lib.measure_fp64_peak(0)}
+
+    if args.only_dense:
+        sizes = [tuple(int(t) for t in args.dense.split(","))] if args.dense else [(100, 100, 4096), (143, 178, 1024),
+                                                                                  (200, 200, 512)]
+        for n, m, B in sizes:
+            print("config 5", json.dumps(dense_config(torch, n, m, B, 1 if args.dense else 2, 1, flush, result["fp64_dfma_peak_tflops"])), flush=True)
+        return 0
 
     # ---- config 1: single Atlas instance -- CPU oracle on one thread (cold / warm-started repeat calls, what the
     # notebook's @benchmark measures, Standing controller.ipynb:149) next to the device latency of a batch of one -----
