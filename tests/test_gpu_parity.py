@@ -116,7 +116,9 @@ def test_acrobot_point_task(orc):
     parity.assert_tick_parity(sub, ref, low.program)
 
 
-@pytest.mark.parametrize("n,m", [(30, 30), (68, 71), (100, 100)])
+# (30,30), (68,71): register tiles; (40,110): shared-memory kernel, 128-thread CTAs; (60,100): shared-memory kernel,
+# 512-thread CTAs (matrices above 100 KB); (100,100): matrices in the per-CTA global scratch, 512-thread CTAs
+@pytest.mark.parametrize("n,m", [(30, 30), (68, 71), (100, 100), (40, 110), (60, 100)])
 def test_dense_qp_batch(orc, n, m):
     from qpcontrol_jl_b200 import _lib
     P, qv, A, l, u = scenarios.synthetic_qps(16, n, m, seed=5)
