@@ -17,7 +17,8 @@ low.set_warm_start(False)
 cg = np.array([list(c.position) + list(c.normal) + [c.mu] for c in low.program.contacts])
 r3 = ctrl.lowlevel(q, v, check=False, task_weight=np.array([e.weight for e in low.program.tasks]), contact_geometry=cg)
 print("atlas", r.status, r2.status, r3.status)
-for n, m in ((30, 30), (68, 71), (2, 3)):
+# register tiles; shared-memory kernel with 128- and 512-thread CTAs; per-CTA global scratch with 512-thread CTAs
+for n, m in ((30, 30), (68, 71), (2, 3), (40, 110), (60, 100), (100, 100)):
     P, qv, A, l, u = scenarios.synthetic_qps(2, n, m, seed=5)
     out = _lib.solve_qp_batch_host(P, qv, A, l, u, settings=st)
     print("dense", n, m, out["status"], out["iters"])
