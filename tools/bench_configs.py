@@ -68,9 +68,13 @@ def tick_config(torch, low, q, v, desired, cw, cm, steps, warmup, flush):
     fn = lambda: dev.solve_device(B, dq, dv, out, desired=dd, contact_weight=dcw, contact_maxnormalforce=dcm,  # noqa: E731
                                   stream=stream)
     ms = timed(fn, steps, warmup, torch, flush)
+    dev.set_profiling(True)  # stage split of one more tick (the library's CUDA events on the same stream)
+    fn()
+    stage = [float(t_) for t_ in dev.stage_times()]
+    dev.set_profiling(False)
     st = out["status"].cpu().numpy()
     it = out["iters"].cpu().numpy()
-    return dict(batch=B, ms_per_tick=ms, solves_per_s=B / (ms * 1e-3), iters_mean=float(it.mean()),
+    return dict(batch=B, ms_per_tick=ms, stage_ms=dict(assemble=stage[0], admm=stage[1], inverse_dynamics=stage[2]), solves_per_s=B / (ms * 1e-3), iters_mean=float(it.mean()),
                 iters_max=int(it.max()), accepted_frac=float(np.mean((st == 1) | (st == 2))),
                 status_counts={int(k): int(c) for k, c in zip(*np.unique(st, return_counts=True))},
                 qp_dims=dict(n=dev.dims["n"], mg=dev.dims["mg"], nbox=dev.dims["nbox"]))
@@ -114,6 +118,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only-dense", action="store_true", help="config 5 only (development: A/B of the large-QP kernels)")
+    ap.add_argument("--only-acrobot", action="store_true", help="config 2 only")
     ap.add_argument("--dense", default=None, help="n,m,B: one size of config 5 (with --only-dense)")
     args = ap.parse_args()
     import torch
@@ -129,6 +134,12 @@ def main():
                                                                                   (200, 200, 512)]
         for n, m, B in sizes:
             print("config 5", json.dumps(dense_config(torch, n, m, B, 1 if args.dense else 2, 1, flush, result["fp64_dfma_peak_tflops"])), flush=True)
+        return 0
+
+    if args.only_acrobot:
+        mech, low, task = scenarios.acrobot_point_task()
+        q, v, des = scenarios.acrobot_random_inputs(mech, 1 << 20, seed=2)
+        print("config 2", json.dumps(tick_config(torch, low, q, v, des, None, None, 3, 2, flush)), flush=True)
         return 0
 
     # ---- config 1: single Atlas instance -- CPU oracle on one thread (cold / warm-started repeat calls, what the
