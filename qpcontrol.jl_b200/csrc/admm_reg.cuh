@@ -32,17 +32,18 @@ namespace qpc {
 #ifndef QPC_REG_PARK
 #define QPC_REG_PARK 10
 #endif
-constexpr int REG_MAXW = 20;  // warps per CTA supported by the reduction scratch
+constexpr int REG_MAXW = 20;  // most warps per CTA of any tile (the reduction scratch holds 16 doubles per warp)
 constexpr int REG_TR = 4;     // rows per thread
 
 // NB = column blocks = lanes per row group (8 or 16); TC = tile columns per thread; NP = NB TC positions
 QPC_HD int admm_reg_positions(int TC, int NB) { return NB * TC; }
 QPC_HD int admm_reg_threads(int TC, int NB) { return (NB * TC / REG_TR) * NB; }  // (NP / 4 row groups) x NB blocks
+QPC_HD int admm_reg_warps(int TC, int NB) { return (admm_reg_threads(TC, NB) + 31) / 32; }
 QPC_HD int admm_reg_smem_doubles(int TC, int NB) {
   const int NP = NB * TC;
   const int NPV = NP + (TC % 4 == 0 ? 2 * NB : 0);  // vectors are padded by 2 per column block when TC % 4 == 0
   // K0 planes are strided by NT + 1 (see RegSolver::KS)
-  return REG_TR * TC * (admm_reg_threads(TC, NB) + 1) + 2 * (2 * NPV + 2) + 2 * NPV + 3 * REG_MAXW * 16 + 13 * NP + 16;
+  return REG_TR * TC * (admm_reg_threads(TC, NB) + 1) + 2 * (2 * NPV + 2) + 2 * NPV + 3 * admm_reg_warps(TC, NB) * 16 + 13 * NP + 16;
 }
 
 #if defined(__CUDACC__)
@@ -64,9 +65,9 @@ __device__ __forceinline__ double warp_sum(double a) {
 // block reduction of KM maxima of non-negative values followed by KS sums; every thread gets the (bitwise identical)
 // result.  `red2` alternates between two buffers so no trailing barrier is needed.
 template <int KM, int KS>
-__device__ __forceinline__ void reg_block_reduce(double (&v)[KM + KS], double* red2, int& sel) {
+__device__ __forceinline__ void reg_block_reduce(double (&v)[KM + KS], double* red2, int& sel, int stride) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  double* red = red2 + sel * (REG_MAXW * 16);
+  double* red = red2 + sel * stride;  // stride = 16 x warps of the CTA
   sel ^= 1;
 #pragma unroll
   for (int k = 0; k < KM + KS; k++) {
@@ -161,6 +162,7 @@ struct RegSolver {
   static_assert(NB == 8 || NB == 16, "lanes per row group");
   static constexpr int NP = NB * TC;               // row / column positions: general rows (mg), x rows (n), padding
   static constexpr int NT = (NP / REG_TR) * NB;    // threads
+  static constexpr int NW = (NT + 31) / 32;        // warps (reduction scratch: 16 doubles per warp and buffer)
   static constexpr int LPR = NB / REG_TR;          // lanes that own the same row (they hold identical row state)
   // K0 (the scaled, unswept matrix) is thread-major: plane (r, c) holds entry (r, c) of every thread's tile.  The plane
   // stride NT + 1 (odd) spreads the scattered 8-byte stores of the load phase (consecutive
@@ -483,8 +485,8 @@ struct RegSolver {
     K0 = smem;
     uv = K0 + TR * TC * KS;        // 2 x PS (sweep) overlaid by 2 x US (iterations)
     cv = uv + 2 * PS;              // 2 x NP
-    red = cv + 2 * NPV;            // 3 x REG_MAXW x 16 (two alternating buffers + the residual check's own)
-    SC = red + 3 * REG_MAXW * 16;  // 13 x NP
+    red = cv + 2 * NPV;            // 3 x NW x 16 (two alternating buffers + the residual check's own)
+    SC = red + 3 * NW * 16;        // 13 x NP
     redsel = 0;
     const int m = mg + nbx;
     // ---- load: coalesced global reads, scattered into the thread-major staging area ----------------------------------
@@ -665,7 +667,7 @@ struct RegSolver {
           v2[0] = fmax(v2[0], cscale * d1 * fabs(QF[fl]));
           v2[1] += cscale * d1 * d1 * fabs(PF[fl]);
         }
-      reg_block_reduce<1, 1>(v2, red, redsel);
+      reg_block_reduce<1, 1>(v2, red, redsel, NW * 16);
       double ct = limit_scaling(n + nel > 0 ? v2[1] / (n + nel) : 1.0);
       const double qn = limit_scaling(v2[0]);
       ct = 1.0 / fmax(ct, qn);
@@ -812,7 +814,7 @@ struct RegSolver {
       } else {
         k0_products(cv, cv + NPV, px, py);
       }
-      double* rbuf = red + 2 * (REG_MAXW * 16);
+      double* rbuf = red + 2 * (NW * 16);
       double pdy = 0.0;  // delta_y projected on the polar of the recession cone (primal infeasibility certificate)
       {
         double ax = hasc ? (isg ? px : cbv * x) : 0.0;
@@ -902,7 +904,7 @@ struct RegSolver {
               gf_transpose_times2(cv + NPV, cv + NPV, uy, uw);
               if ((tid >> 2) < nel) na[0] = fmax(na[0], fabs(uy) / DF[tid >> 2]);
             }
-            reg_block_reduce<1, 0>(na, red, redsel);
+            reg_block_reduce<1, 0>(na, red, redsel, NW * 16);
             if (na[0] < epi * ndy) {
               status = pass ? 3 : -3;
               done = true;
@@ -927,7 +929,7 @@ struct RegSolver {
                   (lo > -QPC_INFTY * QPC_MIN_SCALING && adx < -edi * ndx))
                 nb2[1] = 1.0;
             }
-            reg_block_reduce<2, 0>(nb2, red, redsel);
+            reg_block_reduce<2, 0>(nb2, red, redsel, NW * 16);
             if (nb2[0] < cscale_ * edi * ndx && nb2[1] == 0.0) {
               status = pass ? 4 : -4;
               done = true;

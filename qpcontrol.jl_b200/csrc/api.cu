@@ -42,6 +42,7 @@ struct Backend {
 #include "admm.cuh"
 #include "admm_reg.cuh"
 #include "kin.cuh"
+#include "kin_warp.h"
 #include "setup_api.h"
 
 using namespace qpc;
@@ -123,7 +124,13 @@ struct RegTraits {
 #ifndef QPC_REG_SMALL_TILE
 #define QPC_REG_SMALL_TILE 128
 #endif
-  static constexpr int MAXREG = NB == 16 ? 96 : (TC <= 10 ? QPC_REG_SMALL_TILE : (TC <= 14 ? 255 : 240));
+  // TC <= 4 (KKT systems of up to 32 positions, CTAs of one or two warps): 96 -> 20 instead of 16 one-warp CTAs per SM;
+  // measured on 2^20 Acrobot QPs 21.1 -> 19.5 ms (64 registers: the same there, slower on 4 x 4 tiles, it spills)
+#ifndef QPC_REG_TINY_TILE
+#define QPC_REG_TINY_TILE 96
+#endif
+  static constexpr int MAXREG =
+      NB == 16 ? 96 : (TC <= 4 ? QPC_REG_TINY_TILE : (TC <= 10 ? QPC_REG_SMALL_TILE : (TC <= 14 ? 255 : 240)));
 };
 // ELIM: the leading `nel` variables are eliminated inside the solver (admm_reg.cuh); n stays the caller's dimension
 template <int TC, int NB, bool ELIM = false>
@@ -367,12 +374,18 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
   return e;
 }
 
+// tiny mechanisms run the kinematics kernels one warp per instance (kin_warp.cu)
+static bool kin_warp_per_instance(const DevProgram& p, int ksm) {
+  static const bool on = [] { const char* e = getenv("QPC_KIN_WARP"); return !e || e[0] != '0'; }();
+  return on && p.nb <= KIN_WARP_MAX_BODIES && KIN_WPC * ksm <= KIN_WARP_MAX_SMEM;
+}
 static int configure_kernels(const DevProgram& p) {
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
   const int asmem = admm_smem_doubles(p.n, p.mg, p.nbx) * 8;
   if (ksm > 227 * 1024) return qpc_fail(QPC_ERR_LIMIT, "mechanism does not fit the 227 KB shared memory of one CTA");
   CUDA_TRY(cudaFuncSetAttribute(qpc_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
   CUDA_TRY(cudaFuncSetAttribute(qpc_inverse_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
+  if (kin_warp_per_instance(p, ksm)) CUDA_TRY(kin_warp_configure(ksm));
   if (asmem <= ADMM_BIG_SMEM)
     CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel<ADMM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
   return QPC_OK;
@@ -445,7 +458,9 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
                                  sizeof(double) * cnt * hx->cgstride, cudaMemcpyHostToDevice, s));
     }
     if (timed) cudaEventRecord(c->be.ev[0], s);
-    qpc_assemble_kernel<<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
+    const bool kwarp = kin_warp_per_instance(p, ksm);
+    if (kwarp) CUDA_TRY(kin_warp_assemble(dp, io, qb, lo, hi, ksm, s));
+    else qpc_assemble_kernel<<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
     if (timed) cudaEventRecord(c->be.ev[1], s);
     if (p.n > 0) {
       // Fast path with the diagonal-cost free variables eliminated: only for tolerances above the floor that form puts
@@ -457,7 +472,8 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
     else
       qpc_trivial_status_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, s>>>(qb.status, qb.iters, qb.res, lo, hi);
     if (timed) cudaEventRecord(c->be.ev[2], s);
-    qpc_inverse_dynamics_kernel<<<grid, ID_THREADS, ksm, s>>>(dp, io, qb, tau, vdot, wrench, lo, hi);
+    if (kwarp) CUDA_TRY(kin_warp_inverse_dynamics(dp, io, qb, tau, vdot, wrench, lo, hi, ksm, s));
+    else qpc_inverse_dynamics_kernel<<<grid, ID_THREADS, ksm, s>>>(dp, io, qb, tau, vdot, wrench, lo, hi);
     if (timed) cudaEventRecord(c->be.ev[3], s);
     c->be.launches += 3;
     if (hx) {  // results of this chunk, device staging -> host

@@ -15,7 +15,11 @@
 #define QPC_DEVN __device__ __noinline__
 #define QPC_TID ((int)threadIdx.x)
 #define QPC_NT ((int)blockDim.x)
+#if defined(QPC_WARP_PER_INSTANCE)  // kin_warp.cu: blockDim = (32, instances per CTA), one warp per robot instance
+#define QPC_SYNC() __syncwarp()
+#else
 #define QPC_SYNC() __syncthreads()
+#endif
 #define QPC_LDG(p) __ldg(p)
 #define QPC_UNROLL8 _Pragma("unroll 8")  // product loops: eight loads in flight instead of one dependent load per FMA
 #else
