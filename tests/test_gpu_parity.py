@@ -116,6 +116,29 @@ def test_acrobot_point_task(orc):
     parity.assert_tick_parity(sub, ref, low.program)
 
 
+def test_warp_per_instance_kinematics_equal_the_cta_kernels(tmp_path):
+    """Tiny mechanisms run the kinematics kernels one warp per instance (kin_warp.cu); QPC_KIN_WARP=0 (read once per
+    process, hence the subprocess) forces the CTA-per-instance kernels.  Same code, same arithmetic: identical results,
+    also on an odd batch (the last CTA holds one instance and an idle warp)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "cta.npz")
+    script = ("import sys, numpy as np; sys.path.insert(0, %r); import qpc_loader; qpc_loader.load(); "
+              "from qpcontrol_jl_b200 import scenarios; "
+              "mech, low, task = scenarios.acrobot_point_task(); "
+              "q, v, des = scenarios.acrobot_random_inputs(mech, 1001, seed=12); r = low(q, v, des); "
+              "np.savez(%r, tau=r.tau, vdot=r.vdot, status=r.status, iters=r.iters)" % (root, out))
+    subprocess.run([sys.executable, "-c", script], check=True, env=dict(os.environ, QPC_KIN_WARP="0"), timeout=600)
+    cta = np.load(out)
+    mech, low, task = scenarios.acrobot_point_task()
+    q, v, des = scenarios.acrobot_random_inputs(mech, 1001, seed=12)
+    res = low(q, v, des)
+    assert np.array_equal(res.status, cta["status"]) and np.array_equal(res.iters, cta["iters"])
+    assert np.array_equal(res.tau, cta["tau"]) and np.array_equal(res.vdot, cta["vdot"])
+
+
 # (30,30), (68,71): register tiles; (40,110): shared-memory kernel, 128-thread CTAs; (60,100): shared-memory kernel,
 # 512-thread CTAs (matrices above 100 KB); (100,100): matrices in the per-CTA global scratch, 512-thread CTAs
 @pytest.mark.parametrize("n,m", [(30, 30), (68, 71), (100, 100), (40, 110), (60, 100)])
