@@ -6,7 +6,10 @@
 #include "qpc_program.h"
 
 namespace qpc {
-constexpr int KIN_WPC = 2;                  // instances (warps) per CTA
+#ifndef QPC_KIN_WPC
+#define QPC_KIN_WPC 2
+#endif
+constexpr int KIN_WPC = QPC_KIN_WPC;        // instances (warps) per CTA
 #ifndef QPC_KIN_WARP_MIN_CTAS
 #define QPC_KIN_WARP_MIN_CTAS 10
 #endif
