@@ -170,6 +170,14 @@ int qpc_stage_times(qpc_controller*, double ms[3]);
  * system; qpc_admm_eliminated returns how many variables the next tick eliminates (0 = full system). */
 int qpc_set_admm_elimination(qpc_controller*, int32_t on);
 int qpc_admm_eliminated(const qpc_controller*);
+/* One-warp-per-QP ADMM (csrc/admm_warp.cuh): programs whose general rows are all equalities and determine the unboxed
+ * variables (the StandingController's program: 21 of them, 24 rows) are first reduced to a QP in the <= 32 friction-cone
+ * multipliers alone (Householder QR of the equality block, no KKT system), then iterated with a 32 x 32 operator held in
+ * one warp's registers; OSQP's termination test is evaluated on the full problem.  Instances the reduction cannot
+ * handle are solved by the register-tile kernel in the same tick.  On by default where the program qualifies;
+ * qpc_set_admm_warp(ctrl, 0) forces the KKT-system kernels, qpc_admm_warp reports whether the next tick uses it. */
+int qpc_set_admm_warp(qpc_controller*, int32_t on);
+int qpc_admm_warp(const qpc_controller*);
 /* fp64 FMA throughput of the device in TFLOP/s (dependent-chain-free DFMA loop), the roofline denominator */
 int qpc_measure_fp64_peak(int32_t device, double* tflops);
 

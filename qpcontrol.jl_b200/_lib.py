@@ -60,7 +60,8 @@ SETUP_SYMBOLS = ["qpc_version", "qpc_last_error", "qpc_device_count", "qpc_defau
                  "qpc_standing_setup", "qpc_set_settings", "qpc_finalize", "qpc_controller_dims"]
 COMPUTE_SYMBOLS = ["qpc_solve_batch", "qpc_reserve", "qpc_launch_count", "qpc_assemble_batch", "qpc_solve_qp_batch",
                    "qpc_set_profiling", "qpc_stage_times", "qpc_measure_fp64_peak", "qpc_set_warm_start",
-                   "qpc_reset_warm_start", "qpc_step_batch", "qpc_set_admm_elimination", "qpc_admm_eliminated"]
+                   "qpc_reset_warm_start", "qpc_step_batch", "qpc_set_admm_elimination", "qpc_admm_eliminated",
+                   "qpc_set_admm_warp", "qpc_admm_warp"]
 
 _libs = {}
 
@@ -230,13 +231,16 @@ def _prep_tick_parameters(h: Handles, task_weight, contact_geometry):
 
 def _alloc_out(h: Handles, B):
     return BatchResult(tau=np.zeros((B, h.nv)), vdot=np.zeros((B, h.nv)), wrenches=np.zeros((B, h.ncontacts, 6)),
-                       status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32), residuals=np.zeros((B, 2)))
+                       status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32), residuals=np.zeros((B, 2)),
+                       factorizations=np.zeros(B, np.int32))
 
 
 def _batch_out(res: BatchResult, ptr=lambda a: a.ctypes.data):
     bo = qpc_batch_out()
     bo.tau, bo.vdot, bo.wrench = ptr(res.tau), ptr(res.vdot), ptr(res.wrenches)
     bo.status, bo.iters, bo.residuals = ptr(res.status), ptr(res.iters), ptr(res.residuals)
+    if getattr(res, "factorizations", None) is not None:
+        bo.factorizations = ptr(res.factorizations)
     return bo
 
 
@@ -286,6 +290,14 @@ class DeviceController:
     def admm_eliminated(self) -> int:
         """Number of variables the next tick eliminates from the KKT system (0 = full system)."""
         return int(self.lib.qpc_admm_eliminated(self.h.ctrl))
+
+    def set_admm_warp(self, on: bool):
+        """Allow (default) or forbid the one-warp-per-QP ADMM kernel on the reduced problem."""
+        check(self.lib, self.lib.qpc_set_admm_warp(self.h.ctrl, C.c_int32(int(on))), "qpc_set_admm_warp")
+
+    def admm_warp(self) -> bool:
+        """True when the next tick runs the one-warp-per-QP ADMM kernel."""
+        return bool(self.lib.qpc_admm_warp(self.h.ctrl))
 
     def step_host(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None,
                   task_weight=None, contact_geometry=None):

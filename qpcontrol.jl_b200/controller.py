@@ -38,6 +38,7 @@ class BatchResult:
     status: np.ndarray  # [B] int32, OSQP status codes
     iters: np.ndarray  # [B] int32
     residuals: np.ndarray  # [B, 2] primal, dual (unscaled, OSQP definition on the QP the device solves)
+    factorizations: Optional[np.ndarray] = None  # [B] int32, KKT factorisations (1 + rho updates) of every solve
 
     def contactwrenches(self, program: Program) -> Dict[int, np.ndarray]:
         """`controller.contactwrenches`: per-body sums in world frame (momentum.jl:65-72) -> {body: [B, 6]}."""

@@ -1,0 +1,678 @@
+// admm_warp.cuh -- OSQP-style ADMM, ONE WARP PER QP, the 32 x 32 iteration operator in registers (sm_100a).
+//
+//   min 1/2 x'Px + q'x   s.t.  G x = b (MG equality rows),  lb <= x_b <= ub,   x = (x_a [NA], x_b [nbx <= 32])
+//
+// Device-side replacement for `MOI.optimize!(::OSQP.Optimizer)` reached by `solve!(qpmodel)` (reference
+// src/lowlevel/momentum.jl:58) for controller programs whose general rows are all equalities and whose unboxed variables
+// x_a (free accelerations, task-error slacks: momentum.jl:28,119-126) are determined by those rows (NA <= MG, G_a of
+// full column rank) -- the StandingController's program (standing.jl:31-50) is the model case: NA = 21, MG = 24.
+//
+// Instead of iterating on the (n + m)-dimensional KKT system, the warp first REDUCES the problem (once per solve):
+//   1. Householder QR of G_a applied to [G_a | G_b | b], one matrix column per lane, reflectors broadcast through
+//      shared memory: x_a = xa0 - W x_b and the ME = MG - NA remaining rows A3 x_b = b3 (orthonormalised).
+//   2. H = P_bb + W'P_aa W, h = q_b - W'(P_aa xa0 + q_a): a QP in the nbx friction-cone multipliers alone.
+// and then runs ADMM with the box as the only split constraint; the rows A3 are handled exactly inside the x-update
+// and sigma = 0 (K = H + diag(rho) is positive definite):
+//      x~ = T (rho .* z - y) + t0,    T = K^-1 - K^-1 A3'(A3 K^-1 A3')^-1 A3 K^-1
+//   3. "Factorisation" = in-place Gauss-Jordan inversion of K, row j in the registers of lane j (32 pivots, the pivot
+//      row broadcast through shared memory, one __syncwarp per pivot), then the rank-ME correction.
+//   4. An iteration = lane j's row of T (32 registers) times the vector u = z - y/rho read from shared memory as 16
+//      broadcast 16-byte loads: 32 DFMA per lane, NO cross-lane reduction, one __syncwarp, then relaxation / projection /
+//      dual update in the lane's registers.  The residuals of OSQP's termination test are lane-local quantities
+//      (primal: x~ - z; dual: the stationarity defect of the x-update, y+ - y - rho (x~ - z)) + two redux.sync maxima.
+// Per-row rho (OSQP's rho_vec: equality rows get 1e3 rho) is extended to the active set: rows whose z sits on a bound
+// get kappa rho, interior rows rho / kappa, re-evaluated together with OSQP's residual-balancing rule on a geometric
+// schedule (iterations first, first growth, ...), so the number of refactorisations is bounded and the iteration is a
+// fixed-rho ADMM from then on.  Measured on the 16,384-state Atlas workload (tools/warp_proto.py): 60-80 iterations
+// instead of 218, none above 300 instead of a tail to 5,000.
+//
+// Equality rows hold to rounding for every iterate (they are eliminated), and the eliminated variables' stationarity
+// rows hold exactly by construction, so OSQP's residuals on the full problem are the box rows' (primal) and the x_b
+// rows' (dual); the eps_rel normalisers max(|Ax|, |z|) and max(|Px|, |A'y|, |q|) are evaluated on the full problem.
+// Anything the reduction cannot handle (rank-deficient G_a or A3, a non-positive pivot, infinite bounds, non-finite
+// numbers) is flagged with status QPC_WARP_FALLBACK and appended to a list the register-tile kernel then solves.
+#pragma once
+#include "admm.cuh"
+
+namespace qpc {
+
+constexpr int QPC_WARP_FALLBACK = -99;
+
+struct WarpParams {
+  double kappa;   // rho of rows on a bound = kappa rho, interior rows rho / kappa (1 = OSQP's uniform rho)
+  double growth;  // the adaptation schedule is first, first * growth, ...
+  int first;      // first adaptation iteration
+  int check;      // residual check interval
+};
+
+#if defined(__CUDACC__) || defined(QPC_WARP_EMU)  // QPC_WARP_EMU: tests/emu/warp_emu.cpp runs the body on CPU fibres
+
+// warp-wide maximum of NON-NEGATIVE doubles (NaN sorts above +inf and is therefore propagated): their IEEE bit patterns
+// order like unsigned integers, so two 32-bit redux.sync operations do it
+__device__ __forceinline__ double warp_max_nonneg_w(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
+
+template <int MG, int NA>
+struct WarpSolver {
+  static_assert(NA < 32 && NA <= MG && MG <= 32, "x_a columns plus the right-hand side must fit one column per lane");
+  static constexpr int ME = MG - NA;
+  static constexpr int MEP = ME > 0 ? ME : 1;
+  static constexpr int OFF_H = 0;                     // H, element (i, lane) at i * 32 + lane; setup scratch before
+  static constexpr int OFF_W = OFF_H + 1024;          // W skewed: (k, j) at k * 32 + ((j + k) & 31)
+  static constexpr int OFF_A3 = OFF_W + NA * 32;      // A3 (a, j) at a * 32 + j
+  static constexpr int OFF_U = OFF_A3 + MEP * 32;     // U = A3 K^-1, same layout
+  static constexpr int OFF_V = OFF_U + MEP * 32;      // 2 x 34: iteration vectors / broadcast rows (+ one scalar each)
+  static constexpr int OFF_C = OFF_V + 68;            // xa0 [NA] | g = P_aa xa0 + q_a [NA] | diag P_aa [NA] | q_a [NA]
+  static constexpr int OFF_B3 = OFF_C + 4 * NA;       // b3 [MEP], padded to 4 (4 NA is even: 16-byte alignment holds)
+  static constexpr int OFF_HV = OFF_B3 + ((MEP + 3) & ~3);  // h [32]
+  static constexpr int OFF_RHO = OFF_HV + 32;         // rho_i [32]
+  static constexpr int SMEM_DOUBLES = OFF_RHO + 32;
+  static constexpr unsigned FULL = 0xffffffffu;
+
+  static __device__ __forceinline__ double wsum(double a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(FULL, a, o);
+    return a;
+  }
+  static __device__ __forceinline__ double wmax(double a) { return warp_max_nonneg_w(fabs(a)); }
+
+  // x~ = t0 + T~ u for the vector u at `vec` (32 doubles, 16-byte aligned): four accumulation chains
+  static __device__ __forceinline__ double row_times(const double (&t)[32], const double* vec, double t0) {
+    double a0 = t0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const double2* v2 = reinterpret_cast<const double2*>(vec);
+#pragma unroll
+    for (int c = 0; c < 16; c += 2) {
+      const double2 p = v2[c], q = v2[c + 1];
+      a0 = fma(t[2 * c], p.x, a0);
+      a1 = fma(t[2 * c + 1], p.y, a1);
+      a2 = fma(t[2 * c + 2], q.x, a2);
+      a3 = fma(t[2 * c + 3], q.y, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+  }
+
+  // K = H + diag(rho) -> T~ = T diag(rho) in t[], t0; returns false on a non-positive pivot.  `rho_i` = this lane's rho.
+  static __device__ __forceinline__ bool factor(double* sm, double (&t)[32], double& t0, double rho_i,
+                                                const double (&a3)[MEP], const double (&b3)[MEP], int lane) {
+    double* Hs = sm + OFF_H;
+    double* vb = sm + OFF_V;
+#pragma unroll
+    for (int i = 0; i < 32; i++) t[i] = Hs[i * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+      if (i == lane) t[i] += rho_i;
+    sm[OFF_RHO + lane] = rho_i;
+    // Gauss-Jordan, pivot k at step k.  The pivot row is not scaled in place: lane k keeps its stored row and the
+    // pending factor s = 1 / pivot (applied once at the end); for every other row the update in stored units is the
+    // same formula whether or not the row has been a pivot row already, so the step is branch-free.
+    double s = 1.0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+      double* rb = vb + (k & 1) * 34;
+      if (lane == k) {
+        double2* r2 = reinterpret_cast<double2*>(rb);
+#pragma unroll
+        for (int c = 0; c < 16; c++) r2[c] = make_double2(t[2 * c], t[2 * c + 1]);
+      }
+      __syncwarp();
+      const double piv = rb[k];
+      ok = ok && (piv > 0.0);
+      const double dk = 1.0 / piv;
+      const double m = (lane == k) ? 0.0 : t[k] * dk;
+      const double2* r2 = reinterpret_cast<const double2*>(rb);
+#pragma unroll
+      for (int c = 0; c < 16; c++) {
+        const double2 p = r2[c];
+        if (2 * c != k) t[2 * c] = fma(-m, p.x, t[2 * c]);
+        if (2 * c + 1 != k) t[2 * c + 1] = fma(-m, p.y, t[2 * c + 1]);
+      }
+      t[k] = (lane == k) ? 1.0 : -m;
+      if (lane == k) s = dk;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i++) t[i] *= s;
+    __syncwarp();
+    // rank-ME correction for the rows A3 x = b3:  T = Ki - U' S^-1 U,  U = A3 Ki,  S = U A3'
+    double w[MEP];
+    if constexpr (ME > 0) {
+      double u[ME];
+#pragma unroll
+      for (int a = 0; a < ME; a++) {
+        const double2* r2 = reinterpret_cast<const double2*>(sm + OFF_A3 + a * 32);
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          const double2 p = r2[c];
+          acc0 = fma(t[2 * c], p.x, acc0);
+          acc1 = fma(t[2 * c + 1], p.y, acc1);
+        }
+        u[a] = acc0 + acc1;
+        sm[OFF_U + a * 32 + lane] = u[a];
+      }
+      double S[ME][ME];
+#pragma unroll
+      for (int a = 0; a < ME; a++)
+#pragma unroll
+        for (int b = a; b < ME; b++) S[a][b] = S[b][a] = wsum(a3[a] * u[b]);
+      // S^-1 by Gauss-Jordan (ME x ME, every lane the same arithmetic)
+      double Si[ME][ME];
+#pragma unroll
+      for (int a = 0; a < ME; a++)
+#pragma unroll
+        for (int b = 0; b < ME; b++) Si[a][b] = a == b ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < ME; k++) {
+        ok = ok && (S[k][k] > 0.0);
+        const double d = 1.0 / S[k][k];
+#pragma unroll
+        for (int b = 0; b < ME; b++) {
+          S[k][b] *= d;
+          Si[k][b] *= d;
+        }
+#pragma unroll
+        for (int a = 0; a < ME; a++) {
+          if (a == k) continue;
+          const double f = S[a][k];
+#pragma unroll
+          for (int b = 0; b < ME; b++) {
+            S[a][b] = fma(-f, S[k][b], S[a][b]);
+            Si[a][b] = fma(-f, Si[k][b], Si[a][b]);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < ME; a++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < ME; b++) acc = fma(Si[a][b], u[b], acc);
+        w[a] = acc;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int a = 0; a < ME; a++) {
+        const double2* r2 = reinterpret_cast<const double2*>(sm + OFF_U + a * 32);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          const double2 p = r2[c];
+          t[2 * c] = fma(-w[a], p.x, t[2 * c]);
+          t[2 * c + 1] = fma(-w[a], p.y, t[2 * c + 1]);
+        }
+      }
+    }
+    // t0 = -T h + U' S^-1 b3, then fold rho into the columns
+    {
+      double c0 = 0.0;
+      if constexpr (ME > 0) {
+#pragma unroll
+        for (int a = 0; a < ME; a++) c0 = fma(w[a], b3[a], c0);
+      }
+      t0 = -row_times(t, sm + OFF_HV, -c0);
+      const double2* r2 = reinterpret_cast<const double2*>(sm + OFF_RHO);
+#pragma unroll
+      for (int c = 0; c < 16; c++) {
+        const double2 p = r2[c];
+        t[2 * c] *= p.x;
+        t[2 * c + 1] *= p.y;
+      }
+    }
+    return ok;
+  }
+
+  // dbg (optional, instance `base` only): H [1024] h [32] A3 [ME*32] b3 [ME] xa0 [NA] W [NA*32] cs
+  static __device__ void solve(const Settings& st, const WarpParams& wp, const AdmmProblem& pb, int n, int nbx,
+                               int paa_diag, double* sm, int& fallback, double* dbg) {
+    const int lane = threadIdx.x & 31;
+    const int na = NA;
+    fallback = 0;  // reason code when the instance is handed back: 1 bounds, 2 rank of G_a, 3 rank of A3, 4 cost scale,
+                   // 5 pivot, 6 non-finite residual
+    double* Hs = sm + OFF_H;
+    double* Ws = sm + OFF_W;
+    double* vb = sm + OFF_V;
+    double* Cs = sm + OFF_C;
+    // ---- load: one matrix column per lane -------------------------------------------------------------------------------
+    double ca[MG], cb[MG];  // column `lane` of [G_a | b] (b in lane NA) and of G_b
+    const bool hasb = lane < nbx;
+#pragma unroll
+    for (int r = 0; r < MG; r++) {
+      cb[r] = hasb ? pb.G[(size_t)r * n + na + lane] : 0.0;
+      ca[r] = lane < NA ? pb.G[(size_t)r * n + lane] : (lane == NA ? pb.lg[r] : 0.0);
+    }
+    double lo = hasb ? fmax(pb.lb[lane], -QPC_INFTY) : 0.0;
+    double up = hasb ? fmin(pb.ub[lane], QPC_INFTY) : 0.0;
+    const double qb = hasb ? pb.qv[na + lane] : 0.0;
+    const double qa = lane < NA ? pb.qv[lane] : 0.0;
+    const double paa = lane < NA ? pb.P[(size_t)lane * n + lane] : 0.0;
+    double bn = 0.0;  // |b|_inf
+    if (lane == NA) {
+#pragma unroll
+      for (int r = 0; r < MG; r++) bn = fmax(bn, fabs(ca[r]));
+    }
+    bn = __shfl_sync(FULL, bn, NA);
+    const double qn = wmax(fmax(fabs(qa), fabs(qb)));
+    int bad = (!(lo > -1e19 && up < 1e19) || !(lo <= up)) ? 1 : 0;
+    // ---- Householder QR of G_a, reflectors applied to every column ---------------------------------------------------------
+#pragma unroll
+    for (int k = 0; k < NA; k++) {
+      double* rb = vb + (k & 1) * 34;
+      if (lane == k) {
+        double nrm2 = 0.0;
+#pragma unroll
+        for (int r = k; r < MG; r++) nrm2 = fma(ca[r], ca[r], nrm2);
+        const double nrm = sqrt(nrm2);
+        const double alpha = ca[k] > 0.0 ? -nrm : nrm;
+        const double den = nrm2 - alpha * ca[k];  // = v'v / 2 with v = x - alpha e1
+        rb[k] = ca[k] - alpha;
+#pragma unroll
+        for (int r = k + 1; r < MG; r++) rb[r] = ca[r];
+        rb[MG] = den > 0.0 ? 1.0 / den : 0.0;
+      }
+      __syncwarp();
+      const double beta = rb[MG];
+      double sa = 0.0, sb = 0.0;
+#pragma unroll
+      for (int r = k; r < MG; r++) {
+        const double vr = rb[r];
+        sa = fma(vr, ca[r], sa);
+        sb = fma(vr, cb[r], sb);
+      }
+      sa *= beta;
+      sb *= beta;
+#pragma unroll
+      for (int r = k; r < MG; r++) {  // the reflector is read again rather than kept: 2 MG registers less
+        const double vr = rb[r];
+        ca[r] = fma(-sa, vr, ca[r]);
+        cb[r] = fma(-sb, vr, cb[r]);
+      }
+    }
+    __syncwarp();
+    // R (upper triangle, row-major NA x NA) and 1 / diag into the scratch area; rank test on the diagonal
+    {
+      double dg = 1.0;
+#pragma unroll
+      for (int r = 0; r < NA; r++) {
+        if (lane < NA) Hs[r * NA + lane] = ca[r];
+        if (lane == r) dg = ca[r];
+      }
+      const double ad = lane < NA ? fabs(dg) : 0.0;
+      const double dmax = wmax(ad);
+      double dmin = lane < NA ? ad : 1e300;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
+      if (!(dmin > 1e-11 * dmax) || !finite_val(dmax)) bad = bad ? bad : 2;
+      if (lane < NA) Hs[NA * NA + lane] = 1.0 / dg;
+    }
+    __syncwarp();
+    // back-substitution, two right-hand sides per lane: cb (-> column of W) and ca (lane NA: -> xa0)
+#pragma unroll
+    for (int r = NA - 1; r >= 0; r--) {
+      double s = cb[r], t = ca[r];
+#pragma unroll
+      for (int c = r + 1; c < NA; c++) {
+        const double rv = Hs[r * NA + c];
+        s = fma(-rv, cb[c], s);
+        t = fma(-rv, ca[c], t);
+      }
+      const double ri = Hs[NA * NA + r];
+      cb[r] = s * ri;
+      ca[r] = t * ri;
+    }
+    __syncwarp();
+    // publish W (unpadded copy in the scratch area for the broadcast reads of the H build, skewed copy for later),
+    // xa0, diag P_aa, q_a
+    double* Wu = Hs;
+#pragma unroll
+    for (int k = 0; k < NA; k++) {
+      Wu[k * 32 + lane] = cb[k];
+      Ws[k * 32 + ((lane + k) & 31)] = cb[k];
+      if (lane == NA) Cs[k] = ca[k];
+    }
+    if (lane < NA) {
+      Cs[2 * NA + lane] = paa;
+      Cs[3 * NA + lane] = qa;
+    }
+    __syncwarp();
+    // g = P_aa xa0 + q_a  (lane k < NA)
+    {
+      double g = 0.0;
+      if (lane < NA) {
+        if (paa_diag) {
+          g = fma(paa, Cs[lane], qa);
+        } else {
+          g = qa;
+          for (int l = 0; l < NA; l++) g = fma(pb.P[(size_t)lane * n + l], Cs[l], g);
+        }
+        Cs[NA + lane] = g;
+      }
+    }
+    __syncwarp();
+    // A3 column and b3, orthonormalised rows (modified Gram-Schmidt, two passes)
+    double a3[MEP], b3[MEP];
+    if constexpr (ME > 0) {
+#pragma unroll
+      for (int a = 0; a < ME; a++) {
+        a3[a] = cb[NA + a];
+        b3[a] = __shfl_sync(FULL, ca[NA + a], NA);
+      }
+#pragma unroll
+      for (int a = 0; a < ME; a++) {
+        const double n0 = wsum(a3[a] * a3[a]);
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+          for (int c = 0; c < a; c++) {
+            const double d = wsum(a3[c] * a3[a]);
+            a3[a] = fma(-d, a3[c], a3[a]);
+            b3[a] = fma(-d, b3[c], b3[a]);
+          }
+        }
+        const double n1 = wsum(a3[a] * a3[a]);
+        if (!(n1 > 1e-20 * n0) || !(n0 > 0.0)) bad = bad ? bad : 3;
+        const double inv = 1.0 / sqrt(n1);
+        a3[a] *= inv;
+        b3[a] *= inv;
+      }
+#pragma unroll
+      for (int a = 0; a < ME; a++) {
+        sm[OFF_A3 + a * 32 + lane] = a3[a];
+        if (lane == 0) sm[OFF_B3 + a] = b3[a];
+      }
+    } else {
+      a3[0] = b3[0] = 0.0;
+    }
+    // ---- reduced Hessian column `lane`: P_bb + W'(P_aa W), and h --------------------------------------------------------------
+    double t[32];
+    double hj;
+    {
+      double u[NA];
+      if (paa_diag) {
+#pragma unroll
+        for (int k = 0; k < NA; k++) u[k] = Cs[2 * NA + k] * cb[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < NA; k++) {
+          double acc = 0.0;
+          for (int l = 0; l < NA; l++) acc = fma(pb.P[(size_t)k * n + l], Wu[l * 32 + lane], acc);
+          u[k] = acc;
+        }
+      }
+      {
+        double acc = qb;
+#pragma unroll
+        for (int k = 0; k < NA; k++) acc = fma(-cb[k], Cs[NA + k], acc);
+        hj = acc;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i++)
+        t[i] = (hasb && i < nbx) ? pb.P[(size_t)(na + i) * n + na + lane] : ((i == lane && !hasb) ? 1.0 : 0.0);
+#pragma unroll
+      for (int k = 0; k < NA; k++) {
+        const double2* w2 = reinterpret_cast<const double2*>(Wu + k * 32);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          const double2 p = w2[c];
+          t[2 * c] = fma(p.x, u[k], t[2 * c]);
+          t[2 * c + 1] = fma(p.y, u[k], t[2 * c + 1]);
+        }
+      }
+    }
+    __syncwarp();  // everyone is done reading the scratch copy of W
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      Hs[i * 32 + lane] = t[i];
+      if (i == lane && hasb) tr = t[i];
+    }
+    sm[OFF_HV + lane] = hj;
+    const double cs = wsum(tr) / (nbx > 0 ? nbx : 1);  // cost scale: rho is quoted relative to the mean curvature
+    if (!(cs > 0.0) || !finite_val(cs)) bad = bad ? bad : 4;
+    __syncwarp();
+    if (dbg) {
+      for (int i = 0; i < 32; i++) dbg[i * 32 + lane] = Hs[i * 32 + lane];
+      dbg[1024 + lane] = hj;
+#pragma unroll
+      for (int a = 0; a < ME; a++) dbg[1056 + a * 32 + lane] = a3[a];
+      if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < ME; a++) dbg[1056 + ME * 32 + a] = b3[a];
+        for (int k = 0; k < NA; k++) dbg[1056 + ME * 33 + k] = Cs[k];
+        dbg[1056 + ME * 33 + NA + NA * 32] = cs;
+      }
+      for (int k = 0; k < NA; k++) dbg[1056 + ME * 33 + NA + k * 32 + lane] = Ws[k * 32 + ((lane + k) & 31)];
+    }
+    bad = __reduce_max_sync(FULL, bad);
+    if (bad) {
+      fallback = bad;
+      return;
+    }
+    // ---- ADMM -----------------------------------------------------------------------------------------------------------
+    const bool iseq = (up - lo) < QPC_RHO_TOL;
+    const bool adaptive = st.adaptive_rho != 0;
+    const double kap = adaptive ? wp.kappa : 1.0, kinv = 1.0 / kap;
+    double rho = st.rho * cs;
+    double z = 0.0, yr = 0.0;
+    bool act = false;
+    bool warm = false;
+    if (pb.rho_io && pb.x0 && pb.y0) {
+      const double r = *pb.rho_io;
+      warm = r > 0.0 && r < 1e30;
+      if (warm) {
+        rho = r * cs;
+        z = hasb ? pb.x0[na + lane] : 0.0;
+        act = (z <= lo) || (z >= up);
+      }
+    }
+    auto rho_of = [&](bool active) { return iseq ? QPC_RHO_EQ_FACTOR * rho : (active ? kap * rho : kinv * rho); };
+    double rho_i = rho_of(act);
+    if (warm) yr = (hasb ? pb.y0[MG + lane] : 0.0) / rho_i;
+    double t0 = 0.0;
+    int nfac = 0;
+    int status = -10, iter = 0;
+    int next_adapt = (adaptive && wp.first > 0) ? wp.first : 0x7fffffff;
+    const int chk = wp.check > 0 ? wp.check : 0x7fffffff;
+    int next_chk = chk;
+    const double alpha = st.alpha, oma = 1.0 - st.alpha;
+    double pri_res = 0.0, dua_res = 0.0, xt = 0.0;
+    double ds_last = 1e300;  // last evaluated dual normaliser max(|Px|, |A'y|, |q|)
+    bool refactor = true;
+    for (;;) {
+      if (refactor) {  // the only call site: the inversion is ~1,400 instructions per inlined copy
+        const bool okf = factor(sm, t, t0, rho_i, a3, b3, lane);
+        nfac++;
+        refactor = false;
+        if (!__all_sync(FULL, okf)) {
+          fallback = 5;
+          return;
+        }
+      }
+      // plain iterations up to the next special one
+      const int stop = min(min(next_chk, next_adapt), st.max_iter);
+#pragma unroll 1
+      for (; iter < stop - 1; iter++) {
+        double* ub_ = vb + (iter & 1) * 34;
+        ub_[lane] = z - yr;
+        __syncwarp();
+        xt = row_times(t, ub_, t0);
+        const double w = fma(alpha, xt, fma(oma, z, yr));
+        double zn = w < lo ? lo : w;
+        zn = zn > up ? up : zn;
+        yr = w - zn;
+        z = zn;
+      }
+      if (iter >= st.max_iter) {  // max_iter < 1
+        status = -2;
+        break;
+      }
+      // the special iteration: same update, old values kept for the residuals
+      double* ub_ = vb + (iter & 1) * 34;
+      ub_[lane] = z - yr;
+      __syncwarp();
+      xt = row_times(t, ub_, t0);
+      const double zo = z, yro = yr;
+      {
+        const double w = fma(alpha, xt, fma(oma, z, yr));
+        double zn = w < lo ? lo : w;
+        zn = zn > up ? up : zn;
+        yr = w - zn;
+        z = zn;
+      }
+      iter++;
+      const bool adapt = iter == next_adapt, last = iter >= st.max_iter;
+      const double dy = rho_i * (yr - yro);
+      const double rdv = dy - rho_i * (xt - zo);  // = H x~ + h + A3'nu + y+ : stationarity defect of the x_b rows
+      pri_res = wmax(xt - z);
+      dua_res = wmax(rdv);
+      if (!finite_val(pri_res) || !finite_val(dua_res)) {
+        fallback = 6;
+        return;
+      }
+      const double ps = fmax(bn, fmax(wmax(xt), wmax(z)));
+      const bool pok = pri_res < st.eps_abs + st.eps_rel * ps;
+      bool done = false;
+      if (pok && dua_res < st.eps_abs) {
+        status = 1;
+        done = true;
+      }
+      double ds = ds_last;
+      const bool want_ds = adapt || last || (pok && st.eps_rel > 0.0 && dua_res < st.eps_abs + st.eps_rel * 8.0 * ds_last);
+      if (!done && want_ds) {
+        // full-problem normaliser: x_a = xa0 - W x~;  (Px)_a = P_aa x_a;  (Px)_b = H x~ - W' P_aa W x~;
+        // A'y = -(Px + q) + (0, rdv)  (the x_a rows of the stationarity condition hold exactly)
+        double* xb_ = vb + (iter & 1) * 34;  // the buffer the special iteration did not read
+        xb_[lane] = xt;
+        __syncwarp();
+        const int wrow = lane < NA ? lane : 0;
+        double wx, hx;  // (W x~)_lane for lane < NA, (H x~)_lane
+        {
+          const double2* x2 = reinterpret_cast<const double2*>(xb_);
+          double a0 = 0.0, a1 = 0.0, h0 = 0.0, h1 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 16; c++) {
+            const double2 p = x2[c];
+            a0 = fma(Ws[wrow * 32 + ((2 * c + wrow) & 31)], p.x, a0);
+            a1 = fma(Ws[wrow * 32 + ((2 * c + 1 + wrow) & 31)], p.y, a1);
+            h0 = fma(Hs[(2 * c) * 32 + lane], p.x, h0);
+            h1 = fma(Hs[(2 * c + 1) * 32 + lane], p.y, h1);
+          }
+          wx = lane < NA ? a0 + a1 : 0.0;
+          hx = h0 + h1;
+        }
+        const double xa = lane < NA ? Cs[lane] - wx : 0.0;
+        double pxa = 0.0, pwx = 0.0;  // (P_aa x_a)_lane, (P_aa W x~)_lane
+        if (paa_diag) {
+          pxa = paa * xa;
+          pwx = paa * wx;
+        } else {
+          __syncwarp();
+          xb_[lane] = xa;  // dense P_aa: publish x_a (W x~ = xa0 - x_a)
+          __syncwarp();
+          if (lane < NA)
+            for (int l = 0; l < NA; l++) {
+              const double pv = pb.P[(size_t)lane * n + l];
+              pxa = fma(pv, xb_[l], pxa);
+              pwx = fma(pv, Cs[l] - xb_[l], pwx);
+            }
+        }
+        __syncwarp();
+        xb_[lane] = pwx;
+        __syncwarp();
+        double wtp = 0.0;  // (W' P_aa W x~)_lane
+#pragma unroll
+        for (int k = 0; k < NA; k++) wtp = fma(Ws[k * 32 + ((lane + k) & 31)], xb_[k], wtp);
+        const double pxb = hasb ? hx - wtp : 0.0;
+        const double atya = -(pxa + qa), atyb = hasb ? -(pxb + qb) + rdv : 0.0;
+        ds = fmax(qn, fmax(wmax(fmax(fabs(pxa), fabs(pxb))), wmax(fmax(fabs(atya), fabs(atyb)))));
+        ds_last = ds;
+        __syncwarp();
+      }
+      if (!done && want_ds && pok && dua_res < st.eps_abs + st.eps_rel * ds) {
+        status = 1;
+        done = true;
+      }
+      if (!done && !pok && (iter % 25 == 0 || last)) {
+        // primal infeasibility of {A3 x = b3, lb <= x <= ub}: dy + A3'mu = 0 and u'dy+ + l'dy- + b3'mu < 0
+        const double ndy = wmax(dy);
+        if (ndy > st.eps_prim_inf) {
+          double sup = hasb ? up * fmax(dy, 0.0) + lo * fmin(dy, 0.0) : 0.0;
+          double res = dy;
+          if constexpr (ME > 0) {
+#pragma unroll
+            for (int a = 0; a < ME; a++) {
+              const double mu = -wsum(a3[a] * dy);
+              sup = fma(lane == 0 ? b3[a] : 0.0, mu, sup);
+              res = fma(a3[a], mu, res);
+            }
+          }
+          sup = wsum(sup);
+          if (sup < -st.eps_prim_inf * ndy && wmax(res) < st.eps_prim_inf * ndy) {
+            status = -3;
+            done = true;
+          }
+        }
+      }
+      if (!done && last) {
+        const bool p10 = pri_res < 10.0 * (st.eps_abs + st.eps_rel * ps);
+        const bool d10 = dua_res < 10.0 * (st.eps_abs + st.eps_rel * (ds < 1e299 ? ds : 0.0));
+        status = (p10 && d10) ? 2 : -2;
+        done = true;
+      }
+      if (done) break;
+      if (iter == next_chk) next_chk += chk;
+      if (adapt) {
+        next_adapt = (int)fmin(ceil(next_adapt * wp.growth), 2.0e9);
+        // OSQP's rule without its 1e-10 guards: at tight tolerances (residual / norm ~ 1e-11) they saturate the ratio
+        // and stop rho from growing when the primal residual sits on its rounding floor (~ cond(K) eps |x|)
+        const double prn = pri_res / (ps + 1e-300), drn = dua_res / (ds + 1e-300);
+        double rn = rho * sqrt(prn / (drn + 1e-300));
+        rn = fmin(fmax(rn, QPC_RHO_MIN * cs), QPC_RHO_MAX * cs);
+        const bool big = rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance;
+        const bool an = (z <= lo) || (z >= up);
+        const bool changed = kap != 1.0 && __any_sync(FULL, an != act);
+        if (big || changed) {
+          if (big) rho = rn;
+          act = an;
+          const double rnew = rho_of(act);
+          yr *= rho_i / rnew;  // y is unchanged by a rho update; yr = y / rho follows the new rho
+          rho_i = rnew;
+          refactor = true;
+        }
+      }
+    }
+    // ---- store: x_b = x~ (satisfies the equality rows exactly), x_a = xa0 - W x_b, y_b ----------------------------------------
+    {
+      double* xb_ = vb;
+      __syncwarp();
+      xb_[lane] = xt;
+      __syncwarp();
+      if (lane < NA) {
+        double a0 = Cs[lane];
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) a0 = fma(-Ws[lane * 32 + ((j + lane) & 31)], xb_[j], a0);
+        pb.x[lane] = a0;
+      }
+      if (hasb) {
+        pb.x[na + lane] = xt;
+        if (pb.y) pb.y[MG + lane] = rho_i * yr;
+      }
+      if (pb.y && lane < MG) pb.y[lane] = 0.0;  // multipliers of the eliminated rows are not carried
+      if (lane == 0) {
+        *pb.status = status;
+        if (pb.iters) *pb.iters = iter;
+        if (pb.nfac) *pb.nfac = nfac;
+        if (pb.rho_io) *pb.rho_io = (status == 1 || status == 2) ? rho / cs : -1.0;
+        if (pb.res) {
+          pb.res[0] = pri_res;
+          pb.res[1] = dua_res;
+        }
+      }
+    }
+  }
+};
+
+#endif  // __CUDACC__ || QPC_WARP_EMU
+
+}  // namespace qpc

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -32,6 +33,9 @@ struct Backend {
   bool elimination = true;  // qpc_set_admm_elimination: allow the fast path with eliminated free variables
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int* d_nfac = nullptr;  // [capB] factorisations per instance
+  int* d_fb_list = nullptr;   // [capB] instances the one-warp ADMM kernel handed back (per chunk: its own range of the list)
+  int* d_fb_count = nullptr;  // [NSIDE + 1] their number, per chunk
+  bool warp_admm = true;      // qpc_set_admm_warp: allow the one-warp-per-QP kernel (admm_warp.cuh)
   // chunked tick: sub-batches go to side streams so that one chunk's assembly / inverse dynamics and the tail of its
   // ADMM kernel overlap the next chunk's ADMM kernel
   static constexpr int NSIDE = 4;
@@ -41,6 +45,7 @@ struct Backend {
 
 #include "admm.cuh"
 #include "admm_reg.cuh"
+#include "admm_warp.cuh"
 #include "kin.cuh"
 #include "kin_warp.h"
 #include "setup_api.h"
@@ -90,7 +95,9 @@ __global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 1)
 qpc_admm_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long base, long long B, double* gscratch) {
   extern __shared__ double smem[];
   double* gmat = gscratch ? gscratch + (size_t)blockIdx.x * admm_matrix_doubles(n, mg) : nullptr;
-  for (long long inst = base + blockIdx.x; inst < B; inst += gridDim.x) {
+  const long long cnt = qb.list ? (long long)*qb.list_count : B;
+  for (long long k = base + blockIdx.x; k < cnt; k += gridDim.x) {
+    const long long inst = qb.list ? (long long)qb.list[k] : k;
     AdmmProblem pb;
     pb.P = qb.P + inst * n * n;
     pb.qv = qb.qv + inst * n;
@@ -137,7 +144,9 @@ template <int TC, int NB, bool ELIM = false>
 __global__ void __launch_bounds__((RegTraits<TC, NB>::MAXT)) __maxnreg__((RegTraits<TC, NB>::MAXREG))
 qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long base, long long B, int nel = 0) {
   extern __shared__ double smem[];
-  for (long long inst = base + blockIdx.x; inst < B; inst += gridDim.x) {
+  const long long cnt = qb.list ? (long long)*qb.list_count : B;
+  for (long long k = base + blockIdx.x; k < cnt; k += gridDim.x) {
+    const long long inst = qb.list ? (long long)qb.list[k] : k;
     AdmmProblem pb;
     pb.P = qb.P + inst * n * n;
     pb.qv = qb.qv + inst * n;
@@ -164,6 +173,46 @@ qpc_admm_reg_kernel(Settings st, QpBuffers qb, int n, int mg, int nbx, long long
     s.mg = mg;
     s.nbx = nbx;
     s.solve(st, pb, smem);
+  }
+}
+
+// one warp per QP on the reduced problem (admm_warp.cuh); instances it cannot reduce are appended to fb_list
+#ifndef QPC_WARP_CTAS
+#define QPC_WARP_CTAS 12
+#endif
+template <int MG, int NA>
+__global__ void __launch_bounds__(32, QPC_WARP_CTAS)
+qpc_admm_warp_kernel(Settings st, WarpParams wp, QpBuffers qb, int n, int nbx, long long base, long long B, int paa_diag,
+                     int* fb_list, int* fb_count, double* dbg) {
+  extern __shared__ double smem[];
+  const long long inst = base + blockIdx.x;
+  if (inst >= B) return;
+  const int mg = MG;
+  AdmmProblem pb;
+  pb.P = qb.P + inst * n * n;
+  pb.qv = qb.qv + inst * n;
+  pb.G = qb.G + inst * mg * n;
+  pb.lg = qb.lg + inst * mg;
+  pb.ug = qb.ug + inst * mg;
+  pb.lb = qb.lb + inst * nbx;
+  pb.ub = qb.ub + inst * nbx;
+  pb.x = qb.x + inst * n;
+  pb.y = qb.y ? qb.y + inst * (mg + nbx) : nullptr;
+  pb.status = qb.status + inst;
+  pb.iters = qb.iters ? qb.iters + inst : nullptr;
+  pb.res = qb.res ? qb.res + 2 * inst : nullptr;
+  pb.nfac = qb.nfac ? qb.nfac + inst : nullptr;
+  if (qb.warm) {
+    pb.x0 = pb.x;
+    pb.y0 = pb.y;
+    pb.rho_io = qb.rho + inst;
+  }
+  int fallback = 0;
+  WarpSolver<MG, NA>::solve(st, wp, pb, n, nbx, paa_diag, smem, fallback, inst == base ? dbg : nullptr);
+  if (fallback && threadIdx.x == 0) {
+    *pb.status = QPC_WARP_FALLBACK;
+    if (pb.iters) *pb.iters = -fallback;  // reason code, visible when the hand-back launch is disabled (QPC_WARP_NOFALLBACK)
+    fb_list[atomicAdd(fb_count, 1)] = (int)inst;
   }
 }
 
@@ -229,6 +278,8 @@ static int ensure_capacity(qpc_controller* c, long long B, long long dstride, lo
     CUDA_TRY(grow(b.status, B));
     CUDA_TRY(grow(b.iters, B));
     CUDA_TRY(grow(c->be.d_nfac, B));
+    CUDA_TRY(grow(c->be.d_fb_list, B));
+    if (!c->be.d_fb_count) CUDA_TRY(grow(c->be.d_fb_count, Backend::NSIDE + 1));
     b.capB = B;
     b.cap_desired = 0;
     b.cap_contact = 0;
@@ -264,6 +315,11 @@ static int upload_program(qpc_controller* c) {
 }
 
 static int launch_grid(long long B) { return (int)(B < (1ll << 30) ? B : (1ll << 30)); }
+// grid of an ADMM launch: one CTA per instance, or the bounded persistent grid of list mode
+static int admm_grid(const QpBuffers& qb, long long base, long long B) {
+  const int g = launch_grid(B - base);
+  return (qb.list && qb.list_grid > 0 && qb.list_grid < g) ? qb.list_grid : g;
+}
 
 // ---- ADMM dispatch: register-resident kernel when the KKT matrix fits the register file, shared-memory kernel otherwise
 // returns a code TC * 100 + NB, or 0 for the shared-memory kernel
@@ -301,7 +357,7 @@ static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, in
     if (e != cudaSuccess) return e;
     configured[dev] = bytes;
   }
-  qpc_admm_reg_kernel<TC, NB, ELIM><<<launch_grid(B - base), NT, bytes, stream>>>(st, qb, n, mg, nbx, base, B, nel);
+  qpc_admm_reg_kernel<TC, NB, ELIM><<<admm_grid(qb, base, B), NT, bytes, stream>>>(st, qb, n, mg, nbx, base, B, nel);
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     cudaFuncAttributes fa;
@@ -345,13 +401,13 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
   }
   const int asmem = admm_smem_doubles(n, mg, nbx) * 8;
   if (asmem <= ADMM_BIG_SMEM) {
-    qpc_admm_kernel<ADMM_THREADS><<<launch_grid(B - base), ADMM_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, base, B, nullptr);
+    qpc_admm_kernel<ADMM_THREADS><<<admm_grid(qb, base, B), ADMM_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, base, B, nullptr);
     return cudaGetLastError();
   }
   if (asmem <= 227 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(qpc_admm_kernel<ADMM_BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem);
     if (e != cudaSuccess) return e;
-    qpc_admm_kernel<ADMM_BIG_THREADS><<<launch_grid(B - base), ADMM_BIG_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, base, B, nullptr);
+    qpc_admm_kernel<ADMM_BIG_THREADS><<<admm_grid(qb, base, B), ADMM_BIG_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, base, B, nullptr);
     return cudaGetLastError();
   }
   // QPs that fit neither the register file nor shared memory: matrices in a per-CTA global scratch (L2 resident for
@@ -372,6 +428,61 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
   }
   cudaFreeAsync(scratch, stream);
   return e;
+}
+
+// ---- one-warp-per-QP ADMM (admm_warp.cuh): programs whose unboxed variables are determined by the equality rows ----------
+static WarpParams warp_params() {
+  static const WarpParams wp = [] {
+    WarpParams w;
+    const char* e;
+    w.kappa = (e = getenv("QPC_WARP_KAPPA")) ? atof(e) : 10.0;
+    w.growth = (e = getenv("QPC_WARP_GROWTH")) ? atof(e) : 2.0;
+    w.first = (e = getenv("QPC_WARP_FIRST")) ? atoi(e) : 25;
+    w.check = (e = getenv("QPC_WARP_CHECK")) ? atoi(e) : 5;
+    if (!(w.kappa >= 1.0)) w.kappa = 1.0;
+    if (!(w.growth > 1.0)) w.growth = 2.0;
+    return w;
+  }();
+  return wp;
+}
+// (MG, NA) pairs with an instantiation: code MG * 100 + NA, or 0
+static int warp_shape(const DevProgram& p) {
+  static const bool on = [] { const char* e = getenv("QPC_ADMM_WARP"); return !e || e[0] != '0'; }();
+  if (!on || p.nbx < 1 || p.nbx > 32) return 0;
+  const int na = p.n - p.nbx;
+  if (p.mg == 24 && na == 21) return 2421;  // StandingController on a humanoid with two feet (standing.jl:31-50)
+  return 0;
+}
+static bool paa_is_diagonal(const DevProgram& p) {
+  for (int i = 0; i < p.ntasks; i++)
+    if (!p.tasks[i].eliminated && p.tasks[i].mode == 2) return false;
+  return true;
+}
+template <int MG, int NA>
+static cudaError_t launch_warp_t(const Settings& st, const QpBuffers& qb, int n, int nbx, long long base, long long B,
+                                 int paa_diag, int* fb_list, int* fb_count, double* dbg, cudaStream_t stream) {
+  const int bytes = WarpSolver<MG, NA>::SMEM_DOUBLES * 8;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(qpc_admm_warp_kernel<MG, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(qpc_admm_warp_kernel<MG, NA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  qpc_admm_warp_kernel<MG, NA><<<launch_grid(B - base), 32, bytes, stream>>>(st, warp_params(), qb, n, nbx, base, B, paa_diag,
+                                                                            fb_list, fb_count, dbg);
+  return cudaGetLastError();
+}
+static cudaError_t launch_warp(int shape, const Settings& st, const QpBuffers& qb, int n, int nbx, long long base,
+                               long long B, int paa_diag, int* fb_list, int* fb_count, double* dbg, cudaStream_t stream) {
+  switch (shape) {
+    case 2421: return launch_warp_t<24, 21>(st, qb, n, nbx, base, B, paa_diag, fb_list, fb_count, dbg, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 // tiny mechanisms run the kinematics kernels one warp per instance (kin_warp.cu)
@@ -435,7 +546,7 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
   const bool prof = c->be.profiling;
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
   DeviceBuffers& hb = c->be.buf;
-  auto tick_range = [&](long long lo, long long hi, cudaStream_t s, bool timed) -> int {
+  auto tick_range = [&](long long lo, long long hi, cudaStream_t s, bool timed, int chunk) -> int {
     const int grid = launch_grid(hi - lo);
     const size_t cnt = (size_t)(hi - lo);
     if (hx) {  // inputs of this chunk, host -> device staging
@@ -467,7 +578,45 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
       // on the primal residual, static task weights, and unless QPC_ADMM_ELIM=0
       static const bool elim_on = [] { const char* e = getenv("QPC_ADMM_ELIM"); return !e || e[0] != '0'; }();
       const int nel = (elim_on && c->be.elimination && p.nel > 0 && p.settings.eps_abs >= 1e-6 && !io.tweight) ? p.nel : 0;
-      CUDA_TRY(launch_admm(p.settings, qb, p.n, p.mg, p.nbx, lo, hi, s, nel));
+      const int wshape = c->be.warp_admm ? warp_shape(p) : 0;
+      if (wshape) {
+        // one warp per QP on the reduced problem; what it hands back (rank-deficient reductions, ...) goes through the
+        // register-tile kernel in list mode
+        int* cnt = c->be.d_fb_count + chunk;
+        CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(int), s));
+        // development knobs: QPC_WARP_DEBUG=<file> dumps the reduced problem of the chunk's first instance,
+        // QPC_WARP_NOFALLBACK=1 leaves handed-back instances unsolved (status -99, iters = -reason)
+        static const char* dbg_path = getenv("QPC_WARP_DEBUG");
+        static const bool no_fb = [] { const char* e = getenv("QPC_WARP_NOFALLBACK"); return e && e[0] == '1'; }();
+        double* dbg = nullptr;
+        const int ndbg = 4096;
+        if (dbg_path) {
+          CUDA_TRY(cudaMalloc((void**)&dbg, sizeof(double) * ndbg));
+          CUDA_TRY(cudaMemset(dbg, 0, sizeof(double) * ndbg));
+        }
+        CUDA_TRY(launch_warp(wshape, p.settings, qb, p.n, p.nbx, lo, hi, paa_is_diagonal(p) ? 1 : 0, c->be.d_fb_list + lo,
+                             cnt, dbg, s));
+        if (dbg) {
+          std::vector<double> hd(ndbg);
+          CUDA_TRY(cudaStreamSynchronize(s));
+          CUDA_TRY(cudaMemcpy(hd.data(), dbg, sizeof(double) * ndbg, cudaMemcpyDeviceToHost));
+          cudaFree(dbg);
+          if (FILE* f = fopen(dbg_path, "wb")) {
+            fwrite(hd.data(), sizeof(double), ndbg, f);
+            fclose(f);
+          }
+        }
+        if (!no_fb) {
+          QpBuffers ql = qb;
+          ql.list = c->be.d_fb_list + lo;
+          ql.list_count = cnt;
+          ql.list_grid = 148;
+          CUDA_TRY(launch_admm(p.settings, ql, p.n, p.mg, p.nbx, 0, hi - lo, s, nel));
+          c->be.launches += 1;
+        }
+      } else {
+        CUDA_TRY(launch_admm(p.settings, qb, p.n, p.mg, p.nbx, lo, hi, s, nel));
+      }
     }
     else
       qpc_trivial_status_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, s>>>(qb.status, qb.iters, qb.res, lo, hi);
@@ -494,14 +643,14 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
   // the bulk of the next ADMM kernel.  Results do not depend on the chunking (instances are independent).
   const int nchunk = (!prof && B >= 4096 && c->be.side[0]) ? Backend::NSIDE : 1;
   if (nchunk == 1) {
-    int rc = tick_range(0, B, stream, prof);
+    int rc = tick_range(0, B, stream, prof, Backend::NSIDE);
     if (rc) return rc;
   } else {
     CUDA_TRY(cudaEventRecord(c->be.fork, stream));
     for (int k = 0; k < nchunk; k++) {
       const long long lo = B * k / nchunk, hi = B * (k + 1) / nchunk;
       CUDA_TRY(cudaStreamWaitEvent(c->be.side[k], c->be.fork, 0));
-      int rc = tick_range(lo, hi, c->be.side[k], false);
+      int rc = tick_range(lo, hi, c->be.side[k], false, k);
       if (rc) return rc;
       CUDA_TRY(cudaEventRecord(c->be.join[k], c->be.side[k]));
       CUDA_TRY(cudaStreamWaitEvent(stream, c->be.join[k], 0));
@@ -549,7 +698,7 @@ void qpc_controller_destroy(qpc_controller* c) {
     cudaSetDevice(c->be.device);
     DeviceBuffers& b = c->be.buf;
     void* ptrs[] = {b.P, b.qv, b.G, b.lg, b.ug, b.lb, b.ub, b.des, b.x, b.y, b.q, b.v, b.desired, b.cw,
-                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.tw, b.cg};
+                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.tw, b.cg, c->be.d_fb_list, c->be.d_fb_count};
     for (int i = 0; i < 4; i++)
       if (c->be.ev[i]) cudaEventDestroy(c->be.ev[i]);
     for (void* p : ptrs)
@@ -697,6 +846,18 @@ int qpc_set_admm_elimination(qpc_controller* c, int32_t on) {
   std::lock_guard<std::mutex> lock(c->be.mu);
   c->be.elimination = on != 0;
   return QPC_OK;
+}
+
+int qpc_set_admm_warp(qpc_controller* c, int32_t on) {
+  if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
+  std::lock_guard<std::mutex> lock(c->be.mu);
+  c->be.warp_admm = on != 0;
+  return QPC_OK;
+}
+
+int qpc_admm_warp(const qpc_controller* c) {
+  if (!c || !c->finalized) return 0;
+  return (c->be.warp_admm && warp_shape(c->prog)) ? 1 : 0;
 }
 
 int qpc_admm_eliminated(const qpc_controller* c) {
@@ -1024,7 +1185,7 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
   if (asmem <= ADMM_BIG_SMEM)
     CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel<ADMM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
   QpBuffers qb;
-  memset(&qb, 0, sizeof(qb));
+  qb = QpBuffers();
   if (flags == QPC_DEVICE_PTRS) {
     qb.P = (double*)P;
     qb.qv = (double*)qv;

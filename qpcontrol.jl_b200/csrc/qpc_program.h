@@ -95,6 +95,11 @@ struct QpBuffers {
   int* nfac;    // [B] number of factorisations (1 + rho updates), optional
   double* rho;  // [B] final rho of the slot's last accepted solve (<= 0: none); read when `warm`
   int warm;     // OSQP's implicit warm start: start from x, y, rho of the previous tick of the same slot
+  // list mode (the instances the one-warp kernel handed back): solve instances list[0 .. *list_count) only, on a
+  // bounded persistent grid of list_grid CTAs
+  const int* list = nullptr;
+  const int* list_count = nullptr;
+  int list_grid = 0;
 };
 
 }  // namespace qpc

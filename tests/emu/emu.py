@@ -78,3 +78,44 @@ def solve_qp_batch(P, qv, G, lg, ug, lb=None, ub=None, settings=None, warm=None)
                                              p(out["status"]), p(out["iters"]), p(out["res"]), p(out["rho"])),
             "emu_solve_qp_batch_warm")
     return out
+
+
+_WSO = os.path.join(_HERE, "libqpc_warp_emu.so")
+
+
+def build_warp():
+    deps = [os.path.join(_HERE, "warp_emu.cpp")] + [os.path.join(_CSRC, f) for f in ("admm_warp.cuh", "admm.cuh",
+                                                                                      "qpc_common.h", "qpc_program.h")]
+    if os.path.exists(_WSO) and all(os.path.getmtime(d) <= os.path.getmtime(_WSO) for d in deps):
+        return _WSO
+    subprocess.run(["/usr/bin/g++", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-std=c++17", "-shared",
+                    "-Wno-unknown-pragmas", "-o", _WSO, os.path.join(_HERE, "warp_emu.cpp")], check=True)
+    return _WSO
+
+
+def warp_solve_qp_batch(P, qv, G, lg, lb, ub, settings=None, kappa=10.0, growth=2.0, first=25, check=5, paa_diag=True,
+                        warm=None, debug=False):
+    """The one-warp ADMM kernel body (csrc/admm_warp.cuh, MG = 24, NA = 21) run on 32 CPU fibres per QP."""
+    lib = C.CDLL(build_warp())
+    from qpcontrol_jl_b200 import OSQPSettings
+    st = settings or OSQPSettings()
+    P, qv, G, lg, lb, ub = (L._c(a) for a in (P, qv, G, lg, lb, ub))
+    B, n = qv.shape
+    mg, nbx = lg.shape[1], lb.shape[1]
+    out = dict(x=np.zeros((B, n)), y=np.zeros((B, mg + nbx)), rho=np.zeros(B), status=np.zeros(B, np.int32),
+               iters=np.zeros(B, np.int32), res=np.zeros((B, 2)), nfac=np.zeros(B, np.int32),
+               fallback=np.zeros(B, np.int32), dbg=np.zeros(4096))
+    if warm is not None:
+        out["x"][:], out["y"][:], out["rho"][:] = warm["x"], warm["y"], warm["rho"]
+    p = L._p
+    rc = lib.emu_warp_solve_qp_batch(C.c_int64(B), C.c_int32(n), C.c_int32(mg), C.c_int32(nbx), p(P), p(qv), p(G), p(lg),
+                                     p(lb), p(ub), C.c_double(st.rho), C.c_double(st.alpha), C.c_double(st.eps_abs),
+                                     C.c_double(st.eps_rel), C.c_double(st.eps_prim_inf), C.c_int32(st.max_iter),
+                                     C.c_int32(int(st.adaptive_rho)), C.c_double(st.adaptive_rho_tolerance),
+                                     C.c_double(kappa), C.c_double(growth), C.c_int32(first), C.c_int32(check),
+                                     C.c_int32(int(paa_diag)), C.c_int32(0 if warm is None else 1), p(out["x"]),
+                                     p(out["y"]), p(out["rho"]), p(out["status"]), p(out["iters"]), p(out["res"]),
+                                     p(out["nfac"]), p(out["fallback"]), p(out["dbg"]) if debug else None)
+    if rc != 0:
+        raise RuntimeError("emu_warp_solve_qp_batch: unsupported shape")
+    return out
