@@ -45,6 +45,12 @@ struct WarpParams {
   int check;      // residual check interval
 };
 
+#if defined(__CUDACC__)
+#define QPC_NOINLINE __noinline__
+#else
+#define QPC_NOINLINE
+#endif
+
 #if defined(__CUDACC__) || defined(QPC_WARP_EMU)  // QPC_WARP_EMU: tests/emu/warp_emu.cpp runs the body on CPU fibres
 
 // warp-wide maximum of NON-NEGATIVE doubles (NaN sorts above +inf and is therefore propagated): their IEEE bit patterns
@@ -73,7 +79,9 @@ struct WarpSolver {
   static constexpr int SMEM_DOUBLES = OFF_RHO + 32;
   static constexpr unsigned FULL = 0xffffffffu;
 
-  static __device__ __forceinline__ double wsum(double a) {
+  // warp sum; NOT inlined: ~55 call sites x 25 instructions would otherwise be a fifth of the kernel's code, and the
+  // kernel is instruction-fetch bound before it is anything else (profiles/r2_warp_*)
+  static __device__ QPC_NOINLINE double wsum(double a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(FULL, a, o);
     return a;
@@ -106,12 +114,16 @@ struct WarpSolver {
     for (int i = 0; i < 32; i++)
       if (i == lane) t[i] += rho_i;
     sm[OFF_RHO + lane] = rho_i;
-    // Gauss-Jordan, pivot k at step k.  The pivot row is not scaled in place: lane k keeps its stored row and the
-    // pending factor s = 1 / pivot (applied once at the end); for every other row the update in stored units is the
-    // same formula whether or not the row has been a pivot row already, so the step is branch-free.
+    // Gauss-Jordan, pivot k at step k, as a ROLLED loop (instruction-cache footprint: the unrolled form was 10k
+    // instructions and the kernel stalled 70 % of the time on instruction fetch).  The row registers rotate by one per
+    // step -- the FMA that updates column c writes register c - 1 -- so the pivot column is always register 0 and the
+    // new inverse column enters at register 31; after 32 steps the rotation is the identity.  The pivot row is not
+    // scaled in place: lane k keeps its stored row and the pending factor s = 1 / pivot (applied once at the end); for
+    // every other row the update in stored units is the same formula whether or not the row has been a pivot row
+    // already, so the step is branch-free.
     double s = 1.0;
     bool ok = true;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 32; k++) {
       double* rb = vb + (k & 1) * 34;
       if (lane == k) {
@@ -120,18 +132,20 @@ struct WarpSolver {
         for (int c = 0; c < 16; c++) r2[c] = make_double2(t[2 * c], t[2 * c + 1]);
       }
       __syncwarp();
-      const double piv = rb[k];
+      const double2* r2 = reinterpret_cast<const double2*>(rb);
+      const double2 p0 = r2[0];
+      const double piv = p0.x;
       ok = ok && (piv > 0.0);
       const double dk = 1.0 / piv;
-      const double m = (lane == k) ? 0.0 : t[k] * dk;
-      const double2* r2 = reinterpret_cast<const double2*>(rb);
+      const double m = (lane == k) ? 0.0 : t[0] * dk;
+      t[0] = fma(-m, p0.y, t[1]);
 #pragma unroll
-      for (int c = 0; c < 16; c++) {
+      for (int c = 1; c < 16; c++) {
         const double2 p = r2[c];
-        if (2 * c != k) t[2 * c] = fma(-m, p.x, t[2 * c]);
-        if (2 * c + 1 != k) t[2 * c + 1] = fma(-m, p.y, t[2 * c + 1]);
+        t[2 * c - 1] = fma(-m, p.x, t[2 * c]);
+        t[2 * c] = fma(-m, p.y, t[2 * c + 1]);
       }
-      t[k] = (lane == k) ? 1.0 : -m;
+      t[31] = (lane == k) ? 1.0 : -m;
       if (lane == k) s = dk;
     }
 #pragma unroll
@@ -235,12 +249,27 @@ struct WarpSolver {
     double* vb = sm + OFF_V;
     double* Cs = sm + OFF_C;
     // ---- load: one matrix column per lane -------------------------------------------------------------------------------
+    // G and b are staged through shared memory by a rolled, coalesced copy loop (the unrolled per-row global loads were
+    // 740 instructions of straight-line code)
     double ca[MG], cb[MG];  // column `lane` of [G_a | b] (b in lane NA) and of G_b
     const bool hasb = lane < nbx;
+    {
+      double* Gs = sm + OFF_H;  // [MG][n] then b [MG]; needs MG (n + 1) <= 1024 + 32 NA doubles
+      const int tot = MG * n;
+#pragma unroll 4
+      for (int idx = lane; idx < tot; idx += 32) Gs[idx] = pb.G[idx];
+      if (lane < MG) Gs[tot + lane] = pb.lg[lane];
+      __syncwarp();
+      const double* pa = lane < NA ? Gs + lane : Gs + tot;
+      const int sa_ = lane < NA ? n : 1;
+      const double* pbc = Gs + na + (hasb ? lane : 0);
 #pragma unroll
-    for (int r = 0; r < MG; r++) {
-      cb[r] = hasb ? pb.G[(size_t)r * n + na + lane] : 0.0;
-      ca[r] = lane < NA ? pb.G[(size_t)r * n + lane] : (lane == NA ? pb.lg[r] : 0.0);
+      for (int r = 0; r < MG; r++) {
+        const double va = pa[r * sa_], vb_ = pbc[r * n];
+        ca[r] = lane <= NA ? va : 0.0;
+        cb[r] = hasb ? vb_ : 0.0;
+      }
+      __syncwarp();
     }
     double lo = hasb ? fmax(pb.lb[lane], -QPC_INFTY) : 0.0;
     double up = hasb ? fmin(pb.ub[lane], QPC_INFTY) : 0.0;
@@ -256,70 +285,108 @@ struct WarpSolver {
     const double qn = wmax(fmax(fabs(qa), fabs(qb)));
     int bad = (!(lo > -1e19 && up < 1e19) || !(lo <= up)) ? 1 : 0;
     // ---- Householder QR of G_a, reflectors applied to every column ---------------------------------------------------------
-#pragma unroll
+    // A rolled loop on ROTATING registers (instruction-cache footprint, and no masks): at step k the pivot row is
+    // register 0; the update of row p writes register p - 1, the finished row k goes to shared memory (RA: columns of
+    // [G_a | b], RB: columns of G_b) and a zero enters at register MG - 1.  Retired positions therefore hold zeros in
+    // every column, including the owner's, so the reflector needs no length bookkeeping: v = column - alpha e_0 over all
+    // MG registers.  After NA steps registers 0 .. ME-1 hold the rows that became A3 / b3.
+    constexpr int NAP = NA + 1 + ((NA + 1) & 1);  // row stride of RA and RS (even, >= NA + 1)
+    double* RA = sm + OFF_H;                       // [NA][NAP]: R (upper triangle) and Q1'b in column NA
+    double* RB = RA + NA * NAP;                    // [NA][32]:  Q1'G_b
+    double* RS = RB + NA * 32;                     // [NA][NAP]: R in the order the back-substitution consumes it
+    static_assert(NA * NAP * 2 + NA * 32 <= 1024 + NA * 32, "QR scratch must fit the H and W areas");
+#pragma unroll 1
     for (int k = 0; k < NA; k++) {
       double* rb = vb + (k & 1) * 34;
       if (lane == k) {
         double nrm2 = 0.0;
 #pragma unroll
-        for (int r = k; r < MG; r++) nrm2 = fma(ca[r], ca[r], nrm2);
+        for (int r = 0; r < MG; r++) nrm2 = fma(ca[r], ca[r], nrm2);
         const double nrm = sqrt(nrm2);
-        const double alpha = ca[k] > 0.0 ? -nrm : nrm;
-        const double den = nrm2 - alpha * ca[k];  // = v'v / 2 with v = x - alpha e1
-        rb[k] = ca[k] - alpha;
+        const double alpha = ca[0] > 0.0 ? -nrm : nrm;
+        const double den = nrm2 - alpha * ca[0];  // = v'v / 2 with v = x - alpha e_0
+        rb[0] = ca[0] - alpha;
 #pragma unroll
-        for (int r = k + 1; r < MG; r++) rb[r] = ca[r];
+        for (int r = 1; r < MG; r++) rb[r] = ca[r];
         rb[MG] = den > 0.0 ? 1.0 / den : 0.0;
       }
       __syncwarp();
       const double beta = rb[MG];
       double sa = 0.0, sb = 0.0;
 #pragma unroll
-      for (int r = k; r < MG; r++) {
+      for (int r = 0; r < MG; r++) {
         const double vr = rb[r];
         sa = fma(vr, ca[r], sa);
         sb = fma(vr, cb[r], sb);
       }
       sa *= beta;
       sb *= beta;
-#pragma unroll
-      for (int r = k; r < MG; r++) {  // the reflector is read again rather than kept: 2 MG registers less
-        const double vr = rb[r];
-        ca[r] = fma(-sa, vr, ca[r]);
-        cb[r] = fma(-sb, vr, cb[r]);
+      {
+        const double v0 = rb[0];
+        if (lane <= NA) RA[k * NAP + lane] = fma(-sa, v0, ca[0]);
+        RB[k * 32 + lane] = fma(-sb, v0, cb[0]);
       }
+#pragma unroll
+      for (int r = 1; r < MG; r++) {  // the reflector is read again rather than kept: 2 MG registers less
+        const double vr = rb[r];
+        ca[r - 1] = fma(-sa, vr, ca[r]);
+        cb[r - 1] = fma(-sb, vr, cb[r]);
+      }
+      ca[MG - 1] = 0.0;
+      cb[MG - 1] = 0.0;
     }
     __syncwarp();
-    // R (upper triangle, row-major NA x NA) and 1 / diag into the scratch area; rank test on the diagonal
-    {
-      double dg = 1.0;
+    // the rows that remain: A3 column `lane` and (lane NA) b3
+    double a3[MEP], b3[MEP];
+    if constexpr (ME > 0) {
 #pragma unroll
-      for (int r = 0; r < NA; r++) {
-        if (lane < NA) Hs[r * NA + lane] = ca[r];
-        if (lane == r) dg = ca[r];
+      for (int a = 0; a < ME; a++) {
+        a3[a] = cb[a];
+        b3[a] = __shfl_sync(FULL, ca[a], NA);
       }
-      const double ad = lane < NA ? fabs(dg) : 0.0;
+    } else {
+      a3[0] = b3[0] = 0.0;
+    }
+    // rank test on the diagonal of R; RS[s] holds, for step s of the back-substitution (row r = NA-1-s), R[i-s][r] at
+    // s <= i < NA-1, zero at i < s (solved entries only move), 1 / R[r][r] at NAP-1
+    {
+      const double ad = lane < NA ? fabs(RA[lane * NAP + lane]) : 0.0;
       const double dmax = wmax(ad);
       double dmin = lane < NA ? ad : 1e300;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, o));
       if (!(dmin > 1e-11 * dmax) || !finite_val(dmax)) bad = bad ? bad : 2;
-      if (lane < NA) Hs[NA * NA + lane] = 1.0 / dg;
+      for (int idx = lane; idx < NA * NAP; idx += 32) {
+        const int s_ = idx / NAP, i = idx - s_ * NAP, r = NA - 1 - s_;
+        double val = 0.0;
+        if (i == NAP - 1) val = 1.0 / RA[r * NAP + r];
+        else if (i >= s_ && i - s_ < r) val = RA[(i - s_) * NAP + r];
+        RS[idx] = val;
+      }
     }
     __syncwarp();
-    // back-substitution, two right-hand sides per lane: cb (-> column of W) and ca (lane NA: -> xa0)
+    // Back-substitution, column-oriented on ROTATING registers: at step s the entry to solve sits in register NA-1,
+    // every register moves up by one while the unsolved ones take their update (c[i+1] = c[i] - R[i-s][r] w) and the
+    // result enters at register 0; after NA steps c[r] = w_r.  Two right-hand sides per lane: cb (-> column of W) and
+    // ca (lane NA: -> xa0).
 #pragma unroll
-    for (int r = NA - 1; r >= 0; r--) {
-      double s = cb[r], t = ca[r];
+    for (int r = 0; r < NA; r++) {
+      cb[r] = RB[r * 32 + lane];
+      ca[r] = RA[r * NAP + NA];
+    }
+#pragma unroll 1
+    for (int st_ = 0; st_ < NA; st_++) {
+      const double* rs = RS + st_ * NAP;
+      const double ri = rs[NAP - 1];
+      const double wB = cb[NA - 1] * ri, wA = ca[NA - 1] * ri;
 #pragma unroll
-      for (int c = r + 1; c < NA; c++) {
-        const double rv = Hs[r * NA + c];
-        s = fma(-rv, cb[c], s);
-        t = fma(-rv, ca[c], t);
+      for (int i = NA - 2; i >= 0; i--) {
+        const double rc = rs[i];
+        cb[i + 1] = fma(-rc, wB, cb[i]);
+        ca[i + 1] = fma(-rc, wA, ca[i]);
       }
-      const double ri = Hs[NA * NA + r];
-      cb[r] = s * ri;
-      ca[r] = t * ri;
+      cb[0] = wB;
+      ca[0] = wA;
     }
     __syncwarp();
     // publish W (unpadded copy in the scratch area for the broadcast reads of the H build, skewed copy for later),
@@ -329,7 +396,7 @@ struct WarpSolver {
     for (int k = 0; k < NA; k++) {
       Wu[k * 32 + lane] = cb[k];
       Ws[k * 32 + ((lane + k) & 31)] = cb[k];
-      if (lane == NA) Cs[k] = ca[k];
+      if (lane == 0) Cs[k] = ca[k];  // every lane solved the right-hand side column: xa0
     }
     if (lane < NA) {
       Cs[2 * NA + lane] = paa;
@@ -350,14 +417,8 @@ struct WarpSolver {
       }
     }
     __syncwarp();
-    // A3 column and b3, orthonormalised rows (modified Gram-Schmidt, two passes)
-    double a3[MEP], b3[MEP];
+    // A3 and b3: orthonormalised rows (modified Gram-Schmidt, two passes)
     if constexpr (ME > 0) {
-#pragma unroll
-      for (int a = 0; a < ME; a++) {
-        a3[a] = cb[NA + a];
-        b3[a] = __shfl_sync(FULL, ca[NA + a], NA);
-      }
 #pragma unroll
       for (int a = 0; a < ME; a++) {
         const double n0 = wsum(a3[a] * a3[a]);
@@ -381,52 +442,45 @@ struct WarpSolver {
         sm[OFF_A3 + a * 32 + lane] = a3[a];
         if (lane == 0) sm[OFF_B3 + a] = b3[a];
       }
-    } else {
-      a3[0] = b3[0] = 0.0;
     }
     // ---- reduced Hessian column `lane`: P_bb + W'(P_aa W), and h --------------------------------------------------------------
     double t[32];
-    double hj;
-    {
-      double u[NA];
+    double hj = qb;
+#pragma unroll
+    for (int i = 0; i < 32; i++) t[i] = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < NA; k++) {
+      const double wk = Ws[k * 32 + ((lane + k) & 31)];  // W[k][lane]
+      double u;                                          // (P_aa W)[k][lane]
       if (paa_diag) {
-#pragma unroll
-        for (int k = 0; k < NA; k++) u[k] = Cs[2 * NA + k] * cb[k];
+        u = Cs[2 * NA + k] * wk;
       } else {
-#pragma unroll
-        for (int k = 0; k < NA; k++) {
-          double acc = 0.0;
-          for (int l = 0; l < NA; l++) acc = fma(pb.P[(size_t)k * n + l], Wu[l * 32 + lane], acc);
-          u[k] = acc;
-        }
+        u = 0.0;
+        for (int l = 0; l < NA; l++) u = fma(pb.P[(size_t)k * n + l], Wu[l * 32 + lane], u);
       }
-      {
-        double acc = qb;
+      hj = fma(-wk, Cs[NA + k], hj);
+      const double2* w2 = reinterpret_cast<const double2*>(Wu + k * 32);
 #pragma unroll
-        for (int k = 0; k < NA; k++) acc = fma(-cb[k], Cs[NA + k], acc);
-        hj = acc;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i++)
-        t[i] = (hasb && i < nbx) ? pb.P[(size_t)(na + i) * n + na + lane] : ((i == lane && !hasb) ? 1.0 : 0.0);
-#pragma unroll
-      for (int k = 0; k < NA; k++) {
-        const double2* w2 = reinterpret_cast<const double2*>(Wu + k * 32);
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-          const double2 p = w2[c];
-          t[2 * c] = fma(p.x, u[k], t[2 * c]);
-          t[2 * c + 1] = fma(p.y, u[k], t[2 * c + 1]);
-        }
+      for (int c = 0; c < 16; c++) {
+        const double2 p = w2[c];
+        t[2 * c] = fma(p.x, u, t[2 * c]);
+        t[2 * c + 1] = fma(p.y, u, t[2 * c + 1]);
       }
     }
     __syncwarp();  // everyone is done reading the scratch copy of W
-    double tr = 0.0;
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-      Hs[i * 32 + lane] = t[i];
-      if (i == lane && hasb) tr = t[i];
+    for (int i = 0; i < 32; i++) Hs[i * 32 + lane] = t[i];
+    // + P_bb (rows beyond nbx: identity padding), by a rolled loop: row i of P_bb is read coalesced, which by symmetry is
+    // column i of every lane's row
+    {
+      const double* pp = pb.P + (size_t)na * n + na + lane;
+#pragma unroll 4
+      for (int i = 0; i < 32; i++) {
+        const double pv = (hasb && i < nbx) ? pp[(size_t)i * n] : ((i == lane && !hasb) ? 1.0 : 0.0);
+        Hs[i * 32 + lane] += pv;
+      }
     }
+    const double tr = hasb ? Hs[lane * 32 + lane] : 0.0;
     sm[OFF_HV + lane] = hj;
     const double cs = wsum(tr) / (nbx > 0 ? nbx : 1);  // cost scale: rho is quoted relative to the mean curvature
     if (!(cs > 0.0) || !finite_val(cs)) bad = bad ? bad : 4;
