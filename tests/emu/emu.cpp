@@ -161,4 +161,33 @@ int emu_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const 
   return QPC_OK;
 }
 
+// kinematics + the inverse-dynamics epilogue for given QP solutions x [B][n] (the stage after the ADMM kernel); lets a
+// tick be assembled from emu_assemble_batch + any solver emulation (tests/emu/warp_emu.cpp) + this
+int emu_id_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const double* x, const qpc_batch_out* out) {
+  const DevProgram& p = c->prog;
+  BatchIO io = make_io(in);
+#pragma omp parallel
+  {
+    std::vector<double> ksm(kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N));
+    std::vector<double> tau(p.nv), vd(p.nv), wr(p.ncontacts * 6 + 1);
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t i = 0; i < B; i++) {
+      KinSmem s = kin_layout(ksm.data(), p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N);
+      kin_load(&p, io, i, s);
+      kin_forward(&p, s);
+      kin_composite(&p, s);
+      kin_standing(&p, s);
+      kin_contacts(&p, s);
+      kin_inverse_dynamics(&p, s, x + i * p.n, vd.data(), wr.data(), tau.data());
+      for (int k = 0; k < p.nv; k++) {
+        if (out->tau) out->tau[i * p.nv + k] = tau[k];
+        if (out->vdot) out->vdot[i * p.nv + k] = vd[k];
+      }
+      if (out->wrench)
+        for (int k = 0; k < p.ncontacts * 6; k++) out->wrench[i * p.ncontacts * 6 + k] = wr[k];
+    }
+  }
+  return QPC_OK;
+}
+
 }  // extern "C"

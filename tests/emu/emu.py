@@ -41,6 +41,22 @@ class EmuController:
         L.check(self.lib, self.lib.emu_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo)), "emu_solve_batch")
         return res
 
+    def solve_warp(self, q, v, desired=None, cw=None, cm=None, **warp_kw):
+        """One tick with the ONE-WARP ADMM kernel body (csrc/admm_warp.cuh on CPU fibres) between the emulated assembly
+        and inverse-dynamics stages; `fallback` (reason codes) is attached to the result."""
+        h = self.h
+        a = self.assemble(q, v, desired, cw, cm)
+        w = warp_solve_qp_batch(a["P"], a["q"], a["G"], a["lg"], a["lb"], a["ub"], settings=h.program.settings, **warp_kw)
+        h.sync_defaults()
+        q, v, desired, cw, cm, B = L._prep_host_inputs(h, q, v, desired, cw, cm)
+        res = L._alloc_out(h, B)
+        bi, bo = h.batch_in(q, v, desired, cw, cm), L._batch_out(res)
+        x = np.ascontiguousarray(w["x"])
+        L.check(self.lib, self.lib.emu_id_batch(h.ctrl, C.c_int64(B), C.byref(bi), L._p(x), C.byref(bo)), "emu_id_batch")
+        res.status[:], res.iters[:], res.residuals[:], res.factorizations[:] = w["status"], w["iters"], w["res"], w["nfac"]
+        res.fallback = w["fallback"]
+        return res
+
     def assemble(self, q, v, desired=None, cw=None, cm=None):
         h = self.h
         h.sync_defaults()

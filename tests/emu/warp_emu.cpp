@@ -198,10 +198,10 @@ int emu_warp_solve_qp_batch(int64_t B, int32_t n, int32_t mg, int32_t nbx, const
     pb.iters = iters + i;
     pb.res = res + 2 * i;
     pb.nfac = nfac + i;
+    pb.rho_io = rho_io + i;  // always written; read only on a warm start
     if (warm) {
       pb.x0 = pb.x;
       pb.y0 = pb.y;
-      pb.rho_io = rho_io + i;
     }
     fallback[i] = run_warp<24, 21>(job);
     if (fallback[i]) status[i] = QPC_WARP_FALLBACK;

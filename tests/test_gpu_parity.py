@@ -285,3 +285,88 @@ def test_eliminated_fast_path_reproduces_the_full_system():
     # tight tolerances stay on the full system
     mech2, low2, ctrl2, _ = scenarios.atlas_standing(OSQPSettings.test_suite())
     assert low2.finalize().admm_eliminated() == 0
+
+
+# ---- the one-warp-per-QP ADMM kernel (csrc/admm_warp.cuh): the kernel bench.py times -----------------------------------------
+def _warp_parity(orc, B, seed, masks):
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=seed)
+    cw = cm = None
+    if masks is not None:
+        cm = scenarios.contact_masks(B, 8, p=masks, seed=seed)
+        cw = np.full((B, 8), 1e-3)
+    dev = low.finalize()
+    assert dev.admm_warp(), "the standing program must run the one-warp kernel"
+    res = ctrl(q, v, cw, cm, check=False)
+    oc = orc.OracleController(low.program)
+    ref = oc.solve_batch(q, v, cweight=cw, cmaxnf=cm) if masks is not None else oc.solve_batch(q, v)
+    ok_ref = (ref["status"] == 1) | (ref["status"] == 2)
+    ok_res = (res.status == 1) | (res.status == 2)
+    both = ok_ref & ok_res
+    assert parity.rel_err(res.tau[both], ref["tau"][both]).max() < parity.REL_TOL
+    assert parity.rel_err(res.vdot[both], ref["vd"][both]).max() < parity.REL_TOL
+    assert parity.rel_err(res.wrenches[both], ref["wrenches"][both]).max() < parity.REL_TOL
+    assert np.array_equal(parity.active_sets(res.wrenches[both], low.program), parity.active_sets(ref["wrenches"][both], low.program))
+    assert np.all(res.tau[:, :6] == 0.0)
+    # accept / reject: every disagreement must be an iteration-limit outcome of the ORACLE's lifted-form OSQP (status -2 / 2
+    # after max_iter with residuals still above tolerance) on a state the device converges on -- the reduced form needs
+    # 3-4x fewer iterations and has no instance above 6,000 where the lifted form runs out of its 20,000
+    dis = np.where(ok_ref != ok_res)[0]
+    assert len(dis) <= max(1, B // 500), (len(dis), ref["status"][dis], res.status[dis])
+    for i in dis:
+        assert ref["iters"][i] >= 20000 and res.status[i] == 1, (i, ref["status"][i], ref["iters"][i], res.status[i])
+    assert np.all(res.residuals[ok_res] < 1e-8)
+    return res, ref
+
+
+def test_warp_kernel_matches_oracle_config3_4096(orc):
+    """BASELINE config 3 states, reference test-suite OSQP settings (test/runtests.jl:35-43): the benched kernel directly
+    against the oracle on 4,096 states."""
+    res, ref = _warp_parity(orc, 4096, 3, None)
+    assert np.mean((res.status == 1)) > 0.999
+    assert res.iters.max() < 20000 and res.iters.mean() < 250
+
+
+def test_warp_kernel_matches_oracle_config4_4096(orc):
+    """BASELINE config 4: per-instance active contact sets (test/controller.jl:188-215), 4,096 states."""
+    res, ref = _warp_parity(orc, 4096, 4, 0.75)
+
+
+def test_warp_kernel_agrees_with_kkt_kernels_and_hands_back():
+    """Same solutions as the register-tile KKT kernel (another algorithm for the same QP) to the tolerance both reach, and
+    instances the reduction refuses (here: an infinite maxnormalforce, reason code 1) are solved by that kernel in the
+    same tick."""
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    B = 512
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=8)
+    dev = low.finalize()
+    cw = np.full((B, 8), 1e-3)
+    cm = np.full((B, 8), 1e6)
+    cm[::7, 2] = np.inf
+    rw = ctrl(q, v, cw, cm, check=False)
+    dev.set_admm_warp(False)
+    assert not dev.admm_warp()
+    rk = ctrl(q, v, cw, cm, check=False)
+    dev.set_admm_warp(True)
+    assert np.all(rw.status == 1) and np.all(rk.status == 1)
+    assert parity.rel_err(rw.tau, rk.tau).max() < 1e-6
+    assert parity.rel_err(rw.wrenches, rk.wrenches).max() < 1e-6
+    # handed-back instances went through the KKT kernel: bit-identical to the run with the warp kernel off
+    assert np.array_equal(rw.tau[::7], rk.tau[::7]) and np.array_equal(rw.iters[::7], rk.iters[::7])
+    assert rw.iters[1::7].mean() < 0.5 * rk.iters[1::7].mean()
+
+
+def test_warp_kernel_bench_settings_accuracy(orc):
+    """bench.py's settings (notebook eps = 1e-5): the one-warp kernel is closer to the converged solution than OSQP's own
+    KKT-form iteration is at the same tolerance (its per-row rho identifies the active set)."""
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
+    q, v = scenarios.atlas_random_states(mech, qnom, 2048, seed=3)
+    dev = low.finalize()
+    assert dev.admm_warp()
+    res = ctrl(q, v, check=False)
+    assert np.mean(res.status == 1) > 0.999
+    low.program.settings = OSQPSettings.test_suite()
+    truth = orc.OracleController(low.program).solve_batch(q, v)
+    ok = (res.status == 1) & (truth["status"] == 1)
+    err = parity.rel_err(res.tau[ok], truth["tau"][ok])
+    assert np.median(err) < 5e-5 and np.percentile(err, 99) < 3e-3 and err.max() < 2e-2
