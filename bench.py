@@ -16,8 +16,14 @@ rank owns its own contiguous block of instances (seed offset by rank); nothing i
             flushed between steps), max over ranks.
 `e2e`       the same metric through the reference-facing call with HOST buffers (qpc_solve_batch, QPC_HOST_PTRS):
             pinned host q/v in, tau/vdot/wrenches/status/iters/residuals out, copies inside the timed region.
-`roofline`  dominant kernel (the ADMM solve): SURVEY.md 8(d) algorithmic FLOPs W(n,m,K,R) per solve x batch / its
-            CUDA-event duration, against the fp64 DFMA peak measured live on the same device.
+`roofline`  dominant kernel (the ADMM solve; the one-warp-per-QP kernel for the standing program): the FLOPs its
+            algorithm executes (reduction + R inversions + K iterations, 2 per FMA) x batch / its
+            CUDA-event duration, against the fp64 DFMA peak measured live on the same device.  SURVEY.md 8(d)'s
+            W(n,m,K,R) at the canonical KKT dims is reported beside it (`survey_formula`): that formula prices a KKT
+            iteration the kernel no longer performs, so it is context, not the fraction.
+`config4_strong_split`  BASELINE config 4 (65,536 states with per-instance contact sets, ONE global batch cut into
+            contiguous shards, one per rank): strong scaling, so the N-GPU efficiency measures the machine and not
+            the per-rank seeds.
 `cpu_baseline` / `--impl reference`: oracle/ (CPU fp64 restatement of RBD + Parametron + OSQP, lifted sparse form,
             OpenMP over instances) on the box's host cores -- "port", because Julia / OSQP.jl cannot run here.
 """
@@ -46,6 +52,17 @@ def _env_int(name, default):
         return default
 
 
+def warp_kernel_flops(K, R, MG=24, NA=21, NB=32):
+    """FLOPs (2 per FMA) the one-warp ADMM kernel executes per solve (csrc/admm_warp.cuh), all 32 lanes:
+    Householder QR on rotating registers NA (4 MG + MG/32), back-substitution 2 NA (NA - 1), reduced Hessian NA (NB + 1);
+    per factorisation the 32-pivot Gauss-Jordan NB (NB - 1), the rank-ME correction 2 ME NB and t0 / rho fold 2 NB; per
+    iteration NB FMAs per lane; residual checks are lane-local."""
+    ME = MG - NA
+    setup = NA * (4 * MG + MG / 32.0) + 2 * NA * (NA - 1) + NA * (NB + 1)
+    factor = NB * (NB - 1) + 2 * ME * NB + 2 * NB
+    return 2.0 * 32.0 * (setup + R * factor + K * NB)
+
+
 def algorithmic_flops(n, m, K, R):
     """W(n,m,K,R) = R [n(n+1) m + n^3/3] + K [4nm + 2n^2 + 12(n+m)] + ceil(K/25) [2nm + 2n^2]."""
     return R * (n * (n + 1) * m + n ** 3 / 3.0) + K * (4 * n * m + 2 * n * n + 12 * (n + m)) + \
@@ -69,7 +86,7 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -122,6 +139,12 @@ def build_workload(batch, rank, settings_name):
     return qpc, settings
 
 
+SETTINGS = {"notebook": ("standing_notebook", "eps_abs=eps_rel=1e-5 max_iter=5000 adaptive_rho_interval=25 cold start "
+                         "(notebooks/Standing controller.ipynb:66-71)"),
+            "test_suite": ("test_suite", "eps_abs=1e-8 eps_rel=1e-16 max_iter=20000 adaptive_rho_interval=25 cold start "
+                           "(test/runtests.jl:35-43: the settings at which parity <= 1e-5 is defined and tested)")}
+
+
 def run_reference(args, rank, world):
     """The reference arm: oracle/ on the host cores (all threads), on a bounded sample of the same workload."""
     if rank != 0:
@@ -129,7 +152,7 @@ def run_reference(args, rank, world):
     import qpc_loader
     qpc = qpc_loader.load()
     from oracle import oracle as orc
-    settings = qpc.OSQPSettings.standing_notebook()
+    settings = getattr(qpc.OSQPSettings, SETTINGS[args.settings][0])()
     mech, low, ctrl, qnom = qpc.scenarios.atlas_standing(settings)
     sample = args.cpu_sample
     q, v = qpc.scenarios.atlas_random_states(mech, qnom, sample, seed=3)
@@ -150,7 +173,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "atlas_standing_randomised_states (BASELINE config 3), OSQP eps 1e-5 cold start",
+        "config": {"workload": "atlas_standing_randomised_states (BASELINE config 3)", "osqp": SETTINGS[args.settings][1],
                    "batch_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} instances per step (seed 3), lifted sparse-LDL OSQP restatement, "
@@ -173,6 +196,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="instances per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--masks", action="store_true", help="BASELINE config 4: per-instance active contact sets")
+    ap.add_argument("--settings", default="notebook", choices=sorted(SETTINGS),
+                    help="OSQP settings: the Atlas notebook's (headline) or the reference test suite's (parity tolerance)")
+    ap.add_argument("--config4-batch", type=int, default=65536, help="global batch of the strong-split config 4 leg (0 = skip)")
     ap.add_argument("--as-rank", type=int, default=None, help="development: use the seeds rank R would use (1 GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -196,7 +222,7 @@ def main():
     qpc = qpc_loader.load()
     from qpcontrol_jl_b200 import _lib
 
-    settings = qpc.OSQPSettings.standing_notebook()
+    settings = getattr(qpc.OSQPSettings, SETTINGS[args.settings][0])()
     mech, low, ctrl, qnom = qpc.scenarios.atlas_standing(settings, device=local)
     B = args.batch
     # each rank owns its own block of instances: seed offset = rank (rank 0 = BASELINE config 3's seed 3)
@@ -233,14 +259,14 @@ def main():
         sharding.barrier(cuda)
 
     # ---- device-resident throughput ("value") -----------------------------------------------------------------------
+    sampler = ClockSampler(local)  # started before the warm-up: the timed region is tens of milliseconds
+    sampler.start()
     for _ in range(args.warmup):
         flush.zero_()
         step_device()
     torch.cuda.synchronize()
     launches0 = dev.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
@@ -342,6 +368,51 @@ def main():
                "accepted_frac_last_tick": float(np.mean((seq_ok == 1) | (seq_ok == 2))),
                "note": "warm-started closed loop (qpc_step_batch, device pointers), per rank; not the headline metric"}
 
+    # ---- BASELINE config 4, strong split: ONE global batch of per-instance contact sets, contiguous shard per rank -------
+    c4 = None
+    if args.config4_batch > 0 and not args.masks:
+        G4 = args.config4_batch
+        lo4, hi4 = sharding.shard_range(G4, rank, world)
+        n4 = hi4 - lo4
+        q4, v4 = qpc.scenarios.atlas_random_states(mech, qnom, G4, seed=4)  # every rank draws the same global batch
+        cm4 = qpc.scenarios.contact_masks(G4, len(low.program.contacts), seed=4)
+        dq4, dv4 = torch.from_numpy(q4[lo4:hi4].copy()).to(cuda), torch.from_numpy(v4[lo4:hi4].copy()).to(cuda)
+        dcm4 = torch.from_numpy(cm4[lo4:hi4].copy()).to(cuda)
+        dcw4 = torch.full_like(dcm4, 1e-3)
+        out4 = dict(tau=torch.empty(n4, nv, dtype=torch.float64, device=cuda),
+                    vdot=torch.empty(n4, nv, dtype=torch.float64, device=cuda),
+                    wrench=torch.empty(n4, nc, 6, dtype=torch.float64, device=cuda),
+                    status=torch.empty(n4, dtype=torch.int32, device=cuda),
+                    iters=torch.empty(n4, dtype=torch.int32, device=cuda),
+                    residuals=torch.empty(n4, 2, dtype=torch.float64, device=cuda),
+                    factorizations=torch.empty(n4, dtype=torch.int32, device=cuda))
+        dev.reserve(n4)
+
+        def step4():
+            dev.solve_device(n4, dq4, dv4, out4, contact_weight=dcw4, contact_maxnormalforce=dcm4, stream=stream.cuda_stream)
+
+        for _ in range(3):
+            flush.zero_()
+            step4()
+        n4steps = max(3, min(args.steps, 10))
+        ev4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n4steps)]
+        barrier()
+        for k in range(n4steps):
+            flush.zero_()
+            ev4[k][0].record(stream)
+            step4()
+            ev4[k][1].record(stream)
+        barrier()
+        ms4 = float(np.sum([a.elapsed_time(b) for a, b in ev4]))
+        ms4_max = float(sharding.max_over_ranks([ms4], cuda)[0])
+        st4 = out4["status"].cpu().numpy()
+        acc4 = float(sharding.max_over_ranks([-float(np.mean((st4 == 1) | (st4 == 2)))], cuda)[0])
+        c4 = {"workload": "atlas_standing_varying_contact_sets (BASELINE config 4), each contact on w.p. 0.75, seed 4",
+              "global_batch": G4, "shard": "contiguous blocks (sharding.shard_range), no collective", "scaling": "strong",
+              "steps": n4steps, "ms_per_step": ms4_max / n4steps, "value": G4 * n4steps / (ms4_max * 1e-3), "unit": UNIT,
+              "accepted_frac_min_over_ranks": -acc4, "iters_mean_rank0": float(out4["iters"].cpu().numpy().mean())}
+        del dq4, dv4, dcm4, dcw4, out4
+
     # ---- max over ranks -----------------------------------------------------------------------------------------------------
     ms_total_max, e2e_s_max, admm_ms = [float(x) for x in sharding.max_over_ranks([ms_total, e2e_s, stage[1]], cuda)]
     total_solves = B * world * args.steps
@@ -352,12 +423,21 @@ def main():
         K, R = float(iters.mean()), float(nfac.mean())
         peak_tf = _lib.measure_fp64_peak(local)
         n_c, m_c = 68, 71  # SURVEY.md 8(d) canonical condensed dims
-        nel_x = dev.admm_eliminated()  # fast path: the diagonal-cost free variables are eliminated inside the solver
+        warp = dev.admm_warp()
+        nel_x = 0 if warp else dev.admm_eliminated()  # KKT fast path: diagonal-cost free variables eliminated in the solver
         n_x, m_x = dims["n"] - nel_x, dims["mg"] + dims["nbox"]
         w_canon = float(algorithmic_flops(n_c, m_c, K, R))
-        w_exec = float(algorithmic_flops(n_x, m_x, K, R))
-        ach = w_canon * B / (admm_ms * 1e-3) / 1e12
-        ach_exec = w_exec * B / (admm_ms * 1e-3) / 1e12
+        if warp:
+            w_exec = float(warp_kernel_flops(K, R, MG=dims["mg"], NA=dims["n"] - dims["nbox"]))
+            kernel_name = "qpc_admm_warp_kernel<24,21>"
+            dims_solved = {"reduced_variables": dims["nbox"], "eliminated_by_qr": dims["n"] - dims["nbox"],
+                           "equality_rows": dims["mg"], "box_rows": dims["nbox"]}
+        else:
+            w_exec = float(algorithmic_flops(n_x, m_x, K, R))
+            kernel_name = "qpc_admm_reg_kernel"
+            dims_solved = {"n": n_x, "m": m_x, "eliminated": nel_x}
+        ach = w_exec * B / (admm_ms * 1e-3) / 1e12
+        ach_canon = w_canon * B / (admm_ms * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -367,7 +447,7 @@ def main():
         bytes_per_solve = 1632.0  # q,v,maxnormalforce in; tau,vdot,wrenches,status,iters,res out
         hbm_ach = bytes_per_solve * B / (float(np.mean(ms_steps)) * 1e-3) / 1e9
         traffic = None
-        tf = os.path.join(ROOT, "profiles", "admm_traffic.json")
+        tf = os.path.join(ROOT, "profiles", "admm_warp_traffic.json" if warp else "admm_traffic.json")
         if os.path.exists(tf):
             try:
                 traffic = json.load(open(tf)).get("dram_bytes_per_launch")
@@ -380,8 +460,8 @@ def main():
             "config": {"workload": ("atlas_standing_varying_contact_sets (BASELINE config 4)" if args.masks else
                                     "atlas_standing_randomised_states (BASELINE config 3)"),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"instance-shard x{world}, "
-                       "no collective", "osqp": "eps_abs=eps_rel=1e-5 max_iter=5000 adaptive_rho_interval=25 cold start",
-                       "qp_dims_solved": {"n": n_x, "m": m_x, "eliminated": nel_x}, "l2": "flushed between steps (256 MiB memset)",
+                       "no collective", "osqp": SETTINGS[args.settings][1],
+                       "qp_dims_solved": dims_solved, "l2": "flushed between steps (256 MiB memset)",
                        "model": "atlas-topology 36-DoF humanoid, synthetic inertias (qpcontrol_jl_b200.mechanism.atlas_like)"},
             "per_batch_latency_us": 1e3 * ms_total_max / args.steps,
             "ms_per_step_each": [round(float(x), 3) for x in ms_steps],
@@ -390,19 +470,25 @@ def main():
                     "ms_per_step": 1e3 * e2e_s_max / args.steps, "accepted_frac": e2e_ok},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "qpc_admm_reg_kernel", "achieved": ach, "peak": peak_tf,
+            "roofline": {"bound": "fp64", "kernel": kernel_name, "achieved": ach, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None, "traffic": traffic,
                          "peak_source": "measured live: dependent-chain-free DFMA loop on this device "
                                         "(MEASURED_PEAKS.json carries no fp64 figure)",
-                         "flops_per_solve": w_canon, "dims": {"n": n_c, "m": m_c},
-                         "achieved_executed_dims": ach_exec, "frac_executed_dims": ach_exec / peak_tf if peak_tf else None,
-                         "flops_per_solve_executed_dims": w_exec, "iters_mean": K, "factorizations_mean": R,
+                         "flops_per_solve": w_exec,
+                         "flops_definition": ("FLOPs the kernel's algorithm executes (bench.py: warp_kernel_flops; DESIGN.md 2.3)"
+                                              if warp else "SURVEY.md 8(d) W(n,m,K,R) at the dims the kernel iterates on"),
+                         "survey_formula": {"dims": {"n": n_c, "m": m_c}, "flops_per_solve": w_canon, "achieved": ach_canon,
+                                            "frac": ach_canon / peak_tf if peak_tf else None,
+                                            "note": "SURVEY.md 8(d) W(68,71,K,R) with this kernel's K and R: prices a "
+                                                    "KKT-system iteration; context only when the one-warp kernel runs"},
+                         "iters_mean": K, "factorizations_mean": R,
                          "kernel_ms": admm_ms,
                          "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                                  "bytes_per_solve": bytes_per_solve}},
             "stage_ms": {"assemble": float(stage[0]), "admm": float(stage[1]), "inverse_dynamics": float(stage[2])},
             "accepted_frac": accepted, "iters_max": float(iters.max()), "wall_s_timed_region": wall,
             "sequential_ticks": seq,
+            "config4_strong_split": c4,
         }
         if not args.no_cpu_baseline and world == 1:
             from oracle import oracle as orc
