@@ -532,6 +532,7 @@ struct WarpSolver {
     const double alpha = st.alpha, oma = 1.0 - st.alpha;
     double pri_res = 0.0, dua_res = 0.0, xt = 0.0;
     double ds_last = 1e300;  // last evaluated dual normaliser max(|Px|, |A'y|, |q|)
+    double rp_last = -1.0;   // primal residual at the previous adaptation point
     bool refactor = true;
     for (;;) {
       if (refactor) {  // the only call site: the inversion is ~1,400 instructions per inlined copy
@@ -584,7 +585,8 @@ struct WarpSolver {
         fallback = 6;
         return;
       }
-      const double ps = fmax(bn, fmax(wmax(xt), wmax(z)));
+      const double xzmax = fmax(wmax(xt), wmax(z));
+      const double ps = fmax(bn, xzmax);
       const bool pok = pri_res < st.eps_abs + st.eps_rel * ps;
       bool done = false;
       if (pok && dua_res < st.eps_abs) {
@@ -682,8 +684,14 @@ struct WarpSolver {
         // and stop rho from growing when the primal residual sits on its rounding floor (~ cond(K) eps |x|)
         const double prn = pri_res / (ps + 1e-300), drn = dua_res / (ds + 1e-300);
         double rn = rho * sqrt(prn / (drn + 1e-300));
-        rn = fmin(fmax(rn, QPC_RHO_MIN * cs), QPC_RHO_MAX * cs);
-        const bool big = rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance;
+        // rho floor: the explicit inverse of K = H + diag(rho) puts a rounding floor ~ eps_mach |x| lambda_max(H) / rho_row
+        // on the primal residual (lambda_max <= trace(H) = nbx cs); keep it below eps_abs
+        const double rho_floor = kap * 2.2e-16 * fmax(xzmax, 1.0) * (double)nbx * cs / st.eps_abs;
+        rn = fmin(fmax(rn, fmax(QPC_RHO_MIN * cs, rho_floor)), QPC_RHO_MAX * cs);
+        // a primal residual that has stopped falling since the last adaptation takes any increase of rho, not only 5x ones
+        const bool stalled = !pok && rp_last >= 0.0 && pri_res >= 0.5 * rp_last && rn > 1.5 * rho;
+        rp_last = pri_res;
+        const bool big = stalled || rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance;
         const bool an = (z <= lo) || (z >= up);
         const bool changed = kap != 1.0 && __any_sync(FULL, an != act);
         if (big || changed) {

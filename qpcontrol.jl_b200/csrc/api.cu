@@ -435,7 +435,7 @@ static WarpParams warp_params() {
   static const WarpParams wp = [] {
     WarpParams w;
     const char* e;
-    w.kappa = (e = getenv("QPC_WARP_KAPPA")) ? atof(e) : 10.0;
+    w.kappa = (e = getenv("QPC_WARP_KAPPA")) ? atof(e) : 30.0;
     w.growth = (e = getenv("QPC_WARP_GROWTH")) ? atof(e) : 2.0;
     w.first = (e = getenv("QPC_WARP_FIRST")) ? atoi(e) : 25;
     w.check = (e = getenv("QPC_WARP_CHECK")) ? atoi(e) : 5;

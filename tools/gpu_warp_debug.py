@@ -33,5 +33,5 @@ print("H rel", rel(H, r["H"]), "h rel", rel(h, r["h"]), "xa0 rel", rel(xa0, r["x
 Pd, Pr = A3.T @ A3, r["A3"].T @ r["A3"]
 print("A3 projector rel", rel(Pd, Pr), "A3'b3 rel", rel(A3.T @ b3, r["A3"].T @ r["b3"]), "A3 A3' - I", np.abs(A3 @ A3.T - np.eye(ME)).max())
 print("H sym", np.abs(H - H.T).max(), "finite", np.isfinite(d).all())
-x, stt, it, nf, nad = solve(a["P"][0], a["q"][0], a["G"][0], a["lg"][0], a["lb"][0], a["ub"][0], eps_abs=st.eps_abs, eps_rel=st.eps_rel, max_iter=st.max_iter)
+x, stt, it, nf, nad, nj = solve(a["P"][0], a["q"][0], a["G"][0], a["lg"][0], a["lb"][0], a["ub"][0], eps_abs=st.eps_abs, eps_rel=st.eps_rel, max_iter=st.max_iter)
 print("proto: status", stt, "iters", it, "nfac", nf)

@@ -40,7 +40,7 @@ def reduce_qp(P, q, G, b, nb):
 
 
 def solve(P, q, G, lg, lb, ub, eps_abs=1e-5, eps_rel=1e-5, max_iter=5000, rho0=0.1, alpha=1.6, check=5, tol=5.0,
-          kappa=10.0, first=25, growth=2.0, eq_boost=1e3, eps_pinf=1e-4):
+          kappa=30.0, first=25, growth=2.0, eq_boost=1e3, eps_pinf=1e-4, jump=False):
     nb = lb.shape[0]; n = P.shape[0]; na = n - nb
     r = reduce_qp(P, q, G, lg, nb); H, h, A3, b3, W, xa0 = r["H"], r["h"], r["A3"], r["b3"], r["W"], r["xa0"]
     eq = (ub - lb) < 1e-4
@@ -54,12 +54,14 @@ def solve(P, q, G, lg, lb, ub, eps_abs=1e-5, eps_rel=1e-5, max_iter=5000, rho0=0
     rv, T, t0 = factor(rho, actv); nfac = 1; nadapt = 0
     z = np.zeros(nb); y = np.zeros(nb); bn = np.abs(lg).max()
     nxt = first
-    for it in range(1, max_iter + 1):
+    it = 0; xprev = None; njump = 0; rp_last = None
+    while it < max_iter:
+        it += 1
         v = rv * z - y; xt = T @ v + t0
         zr = alpha * xt + (1 - alpha) * z
         zn = np.clip(zr + y / rv, lb, ub); yn = y + rv * (zr - zn)
-        rdv = yn - y - rv * (xt - z); dy = yn - y; z, y = zn, yn
-        adapt = it == nxt
+        rdv = yn - y - rv * (xt - z); dy = yn - y; zold = z; z, y = zn, yn
+        adapt = it >= nxt
         if it % check and it != max_iter and not adapt: continue
         rp = np.abs(xt - z).max(); rd = np.abs(rdv).max()
         xa = xa0 - W @ xt; x = np.concatenate([xa, xt]); Px = P @ x
@@ -67,24 +69,43 @@ def solve(P, q, G, lg, lb, ub, eps_abs=1e-5, eps_rel=1e-5, max_iter=5000, rho0=0
         ps = max(bn, np.abs(xt).max(), np.abs(z).max()); ds = max(np.abs(Px).max(), np.abs(Aty).max(), np.abs(q).max())
         pok = rp < eps_abs + eps_rel * ps
         if pok and rd < eps_abs + eps_rel * ds:
-            return x, 1, it, nfac, nadapt
+            return x, 1, it, nfac, nadapt, njump
+        # dual drift: z frozen and x~ stationary => y moves by a constant d = dy per iteration (T d = 0) until a clipped row
+        # releases; jump over those iterations (an extrapolation of the dual -- ADMM converges from any (z, y))
+        if jump and not adapt and it < max_iter and np.array_equal(z, zold) and xprev is not None and \
+                np.abs(xt - xprev).max() <= 1e-12 * max(1.0, np.abs(xt).max()):
+            dyr = dy / rv; yr = y / rv
+            lowa = (z <= lb) & (dyr > 0); upa = (z >= ub) & (dyr < 0)
+            m = lowa | upa
+            N = np.inf
+            if m.any():
+                N = np.floor(np.min(-yr[m] / dyr[m])) - 1
+            N = int(min(N, max_iter - 1 - it, (nxt - 1 - it) if nxt > it else 0))
+            if N > 0:
+                y = y + N * dy; it += N; njump += N
+        xprev = xt.copy()
         # primal infeasibility certificate of {A3 x = b3, lb <= x <= ub}: dy + A3'mu = 0, u'dy+ + l'dy- + b3'mu < 0
         ndy = np.abs(dy).max()
         if not pok and ndy > eps_pinf:
             mu = -A3 @ dy
             sup = ub @ np.maximum(dy, 0) + lb @ np.minimum(dy, 0) + b3 @ mu
             if sup < -eps_pinf * ndy and np.abs(dy + A3.T @ mu).max() < eps_pinf * ndy:
-                return x, -3, it, nfac, nadapt
+                return x, -3, it, nfac, nadapt, njump
         if adapt:
             nadapt += 1; nxt = int(np.ceil(nxt * growth))
-            rn = np.clip(rho * np.sqrt((rp / (ps + 1e-300)) / (rd / (ds + 1e-300) + 1e-300)), 1e-6 * cs, 1e6 * cs)  # no 1e-10 guards: they break scale invariance at tight tolerances
+            # rho floor: the explicit inverse T = (H + diag(rho))^-1 carries a rounding floor ~ eps_mach |x| lambda_max / rho_row
+            # on the primal residual; keep it below eps_abs (lambda_max <= trace(H) = nb cs)
+            rho_floor = kappa * 2.2e-16 * max(np.abs(xt).max(), np.abs(z).max(), 1.0) * nb * cs / eps_abs
+            rn = np.clip(rho * np.sqrt((rp / (ps + 1e-300)) / (rd / (ds + 1e-300) + 1e-300)), max(1e-6 * cs, rho_floor), 1e6 * cs)  # no 1e-10 guards: they break scale invariance at tight tolerances
             na_ = (z <= lb) | (z >= ub)
-            big = rn > rho * tol or rn < rho / tol
+            stalled = (not pok) and rp_last is not None and rp >= 0.5 * rp_last and rn > 1.5 * rho
+            rp_last = rp
+            big = rn > rho * tol or rn < rho / tol or stalled
             if big or (kappa != 1.0 and (na_ != actv).any()):
                 if big: rho = rn
                 actv = na_
                 rv, T, t0 = factor(rho, actv); nfac += 1
-    return x, -2, max_iter, nfac, nadapt
+    return x, -2, max_iter, nfac, nadapt, njump
 
 
 if __name__ == "__main__":
@@ -116,7 +137,7 @@ if __name__ == "__main__":
     print("reference statuses:", dict(zip(*np.unique(sr, return_counts=True))))
     base = [admm(*stack(a, i), **kw) for i in range(B)]
     print(f"{'osqp form':30s} iters mean {np.mean([r[3] for r in base]):7.1f} max {np.max([r[3] for r in base]):6d} nfac {np.mean([r[4] for r in base]):.2f}")
-    variants = [(f"k{k:g} f{f} g{g:g}", dict(kappa=k, first=f, growth=g)) for k in (10.0, 30.0) for f, g in ((25, 2.0), (10, 3.0), (20, 2.0))]
+    variants = [(f"k{k:g} f{f} g{g:g}", dict(kappa=k, first=f, growth=g, jump=False)) for k in (10.0, 30.0, 50.0) for f, g in ((25, 2.0), (20, 2.0), (10, 3.0))]
     for name, kk in variants:
         rs = [solve(a["P"][i], a["q"][i], a["G"][i], a["lg"][i], a["lb"][i], a["ub"][i], **{**kw, **kk}) for i in range(B)]
         its = np.array([r[2] for r in rs]); nf = np.array([r[3] for r in rs]); nad = np.array([r[4] for r in rs]); stt = np.array([r[1] for r in rs])
