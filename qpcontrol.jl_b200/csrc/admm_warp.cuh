@@ -62,6 +62,17 @@ __device__ __forceinline__ double warp_max_nonneg_w(double v) {
   return __hiloint2double((int)mh, (int)ml);
 }
 
+// D = A B + C on the fp64 tensor cores: mma.sync m8n8k4 (A 8x4 row-major: lane holds A[lane/4][lane%4]; B 4x8 column-major:
+// lane holds B[lane%4][lane/4]; C/D 8x8: lane holds [lane/4][2 (lane%4) + {0,1}]).  SASS: DMMA.8x8x4.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+#endif
+#ifndef QPC_WARP_DMMA
+#define QPC_WARP_DMMA 1  // reduced Hessian W'(P_aa W) by DMMA (0: DFMA on rotating row registers)
+#endif
+
 template <int MG, int NA>
 struct WarpSolver {
   static_assert(NA < 32 && NA <= MG && MG <= 32, "x_a columns plus the right-hand side must fit one column per lane");
@@ -455,30 +466,62 @@ struct WarpSolver {
     // ---- reduced Hessian column `lane`: P_bb + W'(P_aa W), and h --------------------------------------------------------------
     double t[32];
     double hj = qb;
+    if (QPC_WARP_DMMA && paa_diag) {
+      // W'(P_aa W) as 4 x 4 tiles of 8 x 8 on the fp64 tensor cores: 96 DMMA.8x8x4 instead of 672 DFMA per lane (the
+      // kernel is bound by issue slots and latency, not by the fp64 pipe: profiles/r2_warp_dmma_*).  Operands come from the
+      // skewed W in shared memory; the accumulator fragments go straight to H in shared memory.
+      const int gid = lane >> 2, tig = lane & 3;
+      constexpr int KS = (NA + 3) / 4;
+      double aw[4][KS], pk[KS];
 #pragma unroll
-    for (int i = 0; i < 32; i++) t[i] = 0.0;
+      for (int ks = 0; ks < KS; ks++) {
+        const int k = 4 * ks + tig;
+        const bool valid = k < NA;
+        const int kk = valid ? k : 0;
+        pk[ks] = valid ? Cs[2 * NA + kk] : 0.0;
+#pragma unroll
+        for (int tq = 0; tq < 4; tq++) aw[tq][ks] = valid ? Ws[kk * 32 + ((8 * tq + gid + kk) & 31)] : 0.0;
+      }
 #pragma unroll 1
-    for (int k = 0; k < NA; k++) {
-      const double wk = Ws[k * 32 + ((lane + k) & 31)];  // W[k][lane]
-      double u;                                          // (P_aa W)[k][lane]
-      if (paa_diag) {
-        u = Cs[2 * NA + k] * wk;
-      } else {
-        u = 0.0;
-        for (int l = 0; l < NA; l++) u = fma(pb.P[(size_t)k * n + l], Wu[l * 32 + lane], u);
-      }
-      hj = fma(-wk, Cs[NA + k], hj);
-      const double2* w2 = reinterpret_cast<const double2*>(Wu + k * 32);
+      for (int k = 0; k < NA; k++) hj = fma(-Ws[k * 32 + ((lane + k) & 31)], Cs[NA + k], hj);
+      __syncwarp();  // the scratch copy of W in the H area is dead (the A3 orthonormalisation was its last barrier)
 #pragma unroll
-      for (int c = 0; c < 16; c++) {
-        const double2 p = w2[c];
-        t[2 * c] = fma(p.x, u, t[2 * c]);
-        t[2 * c + 1] = fma(p.y, u, t[2 * c + 1]);
+      for (int ti = 0; ti < 4; ti++) {
+#pragma unroll
+        for (int tj = 0; tj < 4; tj++) {
+          double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) dmma884(c0, c1, aw[ti][ks], pk[ks] * aw[tj][ks]);
+          *reinterpret_cast<double2*>(Hs + (8 * ti + gid) * 32 + 8 * tj + 2 * tig) = make_double2(c0, c1);
+        }
       }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i++) t[i] = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < NA; k++) {
+        const double wk = Ws[k * 32 + ((lane + k) & 31)];  // W[k][lane]
+        double u;                                          // (P_aa W)[k][lane]
+        if (paa_diag) {
+          u = Cs[2 * NA + k] * wk;
+        } else {
+          u = 0.0;
+          for (int l = 0; l < NA; l++) u = fma(pb.P[(size_t)k * n + l], Wu[l * 32 + lane], u);
+        }
+        hj = fma(-wk, Cs[NA + k], hj);
+        const double2* w2 = reinterpret_cast<const double2*>(Wu + k * 32);
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          const double2 p = w2[c];
+          t[2 * c] = fma(p.x, u, t[2 * c]);
+          t[2 * c + 1] = fma(p.y, u, t[2 * c + 1]);
+        }
+      }
+      __syncwarp();  // everyone is done reading the scratch copy of W
+#pragma unroll
+      for (int i = 0; i < 32; i++) Hs[i * 32 + lane] = t[i];
     }
-    __syncwarp();  // everyone is done reading the scratch copy of W
-#pragma unroll
-    for (int i = 0; i < 32; i++) Hs[i * 32 + lane] = t[i];
     // + P_bb (rows beyond nbx: identity padding), by a rolled loop: row i of P_bb is read coalesced, which by symmetry is
     // column i of every lane's row
     {

@@ -89,6 +89,19 @@ struct double2 {
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 using std::max;
 using std::min;
+// mma.sync.m8n8k4.f64 on the fibres: A[lane/4][lane%4], B[lane%4][lane/4] published, D[lane/4][2 (lane%4) + {0,1}] computed
+static inline void dmma884(double& d0, double& d1, double a, double b) {
+  const int me = emu::g_lane, buf = emu::g_phase[me]++ & 1;
+  static double sa[2][emu::W], sb[2][emu::W];
+  sa[buf][me] = a;
+  sb[buf][me] = b;
+  emu::yield_lane();
+  const int row = me >> 2, c0 = 2 * (me & 3);
+  for (int k = 0; k < 4; k++) {
+    d0 = fma(sa[buf][row * 4 + k], sb[buf][c0 * 4 + k], d0);
+    d1 = fma(sa[buf][row * 4 + k], sb[buf][(c0 + 1) * 4 + k], d1);
+  }
+}
 
 #include "../../qpcontrol.jl_b200/csrc/admm_warp.cuh"
 
