@@ -91,12 +91,18 @@ typedef struct {
   /* Remaining per-tick Parameters of the reference; both may be NULL (= setup-time values): */
   const double* task_weight;      /* [B][task_weight_stride] scalar weight of every task in addtask! order -- a
                                      Parameter-valued `weight` of addtask!(controller, task, weight), momentum.jl:107-110;
-                                     entries of hard and matrix-weighted tasks are ignored */
+                                     entries of hard and matrix-weighted tasks are ignored (matrix weights: below) */
   int64_t task_weight_stride;     /* >= ntasks, or 0 to broadcast one row */
   const double* contact_geometry; /* [B][contact_geometry_stride]: per contact position[3], normal[3] (body frame) and
                                      mu -- ContactPoint.position / .normal / .mu as Parameters, contacts.jl:39,53-61;
                                      exercised by test/controller.jl:42-47,110-118 */
   int64_t contact_geometry_stride; /* >= 7 * ncontacts, or 0 to broadcast one row */
+  const double* task_weight_matrix; /* [B][task_weight_matrix_stride]: the dim x dim weights (row-major) of the
+                                     matrix-weighted tasks, concatenated in addtask! order -- a Parameter-valued matrix
+                                     `weight` of addtask!(controller, task, weight), momentum.jl:113-117, exercised by
+                                     test/controller.jl:232-285; NULL = the matrices given at setup.  The Hessian block of
+                                     the task's slack is W + W' (an unsymmetric W is allowed, as in the reference) */
+  int64_t task_weight_matrix_stride; /* >= qpc_controller_weight_matrix_doubles(), or 0 to broadcast one row */
 } qpc_batch_in;
 
 /* Outputs of one batched tick: what the reference leaves in tau (momentum.jl:75-80), controller.result.vd (:62-64)
@@ -151,6 +157,8 @@ int qpc_finalize(qpc_controller*, int32_t device);
 /* sizes: nq, nv, ndes, ncontacts, and the dims (n, m_general, n_box) of the condensed QP the device solves */
 int qpc_controller_dims(const qpc_controller*, int32_t* nq, int32_t* nv, int32_t* ndes, int32_t* ncontacts,
                         int32_t* n, int32_t* mg, int32_t* nbox);
+/* nwmat: doubles of one row of qpc_batch_in.task_weight_matrix (sum of dim^2 over the matrix-weighted tasks) */
+int qpc_controller_weight_matrix_doubles(const qpc_controller*);
 
 /* ---- the control tick for B instances: (controller)(tau, t, x) (momentum.jl:41-81 / standing.jl:58-89) ------------ */
 int qpc_solve_batch(qpc_controller*, int64_t B, const qpc_batch_in*, const qpc_batch_out*, int32_t flags,

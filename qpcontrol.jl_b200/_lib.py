@@ -12,6 +12,7 @@ from typing import Optional
 
 import numpy as np
 
+from .program import MATRIX_WEIGHT
 from .controller import BatchResult
 from .program import OSQPSettings, Program
 
@@ -46,7 +47,8 @@ class qpc_batch_in(C.Structure):
     _fields_ = [("q", C.c_void_p), ("v", C.c_void_p), ("desired", C.c_void_p), ("desired_stride", C.c_int64),
                 ("contact_weight", C.c_void_p), ("contact_maxnormalforce", C.c_void_p), ("contact_stride", C.c_int64),
                 ("task_weight", C.c_void_p), ("task_weight_stride", C.c_int64),
-                ("contact_geometry", C.c_void_p), ("contact_geometry_stride", C.c_int64)]
+                ("contact_geometry", C.c_void_p), ("contact_geometry_stride", C.c_int64),
+                ("task_weight_matrix", C.c_void_p), ("task_weight_matrix_stride", C.c_int64)]
 
 
 class qpc_batch_out(C.Structure):
@@ -57,7 +59,8 @@ class qpc_batch_out(C.Structure):
 SETUP_SYMBOLS = ["qpc_version", "qpc_last_error", "qpc_device_count", "qpc_default_settings", "qpc_mechanism_create",
                  "qpc_mechanism_destroy", "qpc_mechanism_dims", "qpc_controller_create", "qpc_controller_destroy",
                  "qpc_add_contact", "qpc_set_contact_params", "qpc_add_task", "qpc_set_task_desired", "qpc_regularize",
-                 "qpc_standing_setup", "qpc_set_settings", "qpc_finalize", "qpc_controller_dims"]
+                 "qpc_standing_setup", "qpc_set_settings", "qpc_finalize", "qpc_controller_dims",
+                 "qpc_controller_weight_matrix_doubles"]
 COMPUTE_SYMBOLS = ["qpc_solve_batch", "qpc_reserve", "qpc_launch_count", "qpc_assemble_batch", "qpc_solve_qp_batch",
                    "qpc_set_profiling", "qpc_stage_times", "qpc_measure_fp64_peak", "qpc_set_warm_start",
                    "qpc_reset_warm_start", "qpc_step_batch", "qpc_set_admm_elimination", "qpc_admm_eliminated",
@@ -177,7 +180,7 @@ class Handles:
 
     # ---- argument marshalling shared by every compute entry point ----------------------------------------------
     def batch_in(self, q, v, desired, cw, cm, ptr=lambda a: a.ctypes.data, keep=None, task_weight=None,
-                 contact_geometry=None):
+                 contact_geometry=None, task_weight_matrix=None):
         """Builds a qpc_batch_in from arrays (numpy for host pointers; `ptr` extracts the address).  task_weight
         [B, ntasks] / [ntasks] and contact_geometry [B, ncontacts, 7] / [ncontacts, 7] are the per-tick Parameters of
         the reference (task weights; contact position, normal, mu)."""
@@ -196,6 +199,9 @@ class Handles:
         if contact_geometry is not None:
             bi.contact_geometry = ptr(contact_geometry)
             bi.contact_geometry_stride = 0 if contact_geometry.ndim == 2 else contact_geometry.shape[1] * 7
+        if task_weight_matrix is not None:
+            bi.task_weight_matrix = ptr(task_weight_matrix)
+            bi.task_weight_matrix_stride = 0 if task_weight_matrix.ndim == 1 else task_weight_matrix.shape[1]
         return bi
 
 
@@ -217,16 +223,38 @@ def _prep_host_inputs(h: Handles, q, v, desired, cw, cm):
             cw = np.ascontiguousarray(np.broadcast_to(cw, cm.shape))
         else:
             cm = np.ascontiguousarray(np.broadcast_to(cm, cw.shape))
+    _check_rows(B, desired=(desired, 1), contact_weight=(cw, 1), contact_maxnormalforce=(cm, 1))
+    if cw is not None and cw.shape[-1] != h.ncontacts:
+        raise ValueError(f"contact arrays must have {h.ncontacts} columns")
     return q, v, desired, cw, cm, B
 
 
-def _prep_tick_parameters(h: Handles, task_weight, contact_geometry):
-    tw, cg = _c(task_weight), _c(contact_geometry)
+def _check_rows(B, **arrays):
+    """Per-instance arrays must have exactly B rows: the C ABI copies B * stride doubles from them (a shorter array would
+    be read out of bounds).  `base_ndim` = the number of dimensions of ONE row (a broadcast row has that many)."""
+    for name, (a, base_ndim) in arrays.items():
+        if a is None or a.ndim == base_ndim:
+            continue
+        if a.ndim != base_ndim + 1 or a.shape[0] != B:
+            raise ValueError(f"{name} must have one row per instance ({B}) or be a single broadcast row; got {a.shape}")
+
+
+def _prep_tick_parameters(h: Handles, task_weight, contact_geometry, B=None, task_weight_matrix=None):
+    tw, cg, twm = _c(task_weight), _c(contact_geometry), _c(task_weight_matrix)
     if tw is not None and tw.shape[-1] != len(h.program.tasks):
         raise ValueError(f"task_weight must have {len(h.program.tasks)} columns (one per task, addtask! order)")
     if cg is not None and cg.shape[-2:] != (h.ncontacts, 7):
         raise ValueError(f"contact_geometry must be [..., {h.ncontacts}, 7] (position, normal, mu per contact)")
-    return tw, cg
+    if twm is not None:
+        nw = sum(e.task.dimension ** 2 for e in h.program.tasks if e.mode == MATRIX_WEIGHT)
+        if twm.shape[-1] != nw:
+            raise ValueError(f"task_weight_matrix must have {nw} columns: the dim x dim weights (row-major) of the "
+                             "matrix-weighted tasks, concatenated in addtask! order")
+    if B is not None:
+        _check_rows(B, task_weight=(tw, 1), contact_geometry=(cg, 2), task_weight_matrix=(twm, 1))
+    if task_weight_matrix is None:
+        return tw, cg
+    return tw, cg, twm
 
 
 def _alloc_out(h: Handles, B):
@@ -332,14 +360,18 @@ class DeviceController:
                                                 C.c_int32(DEVICE_PTRS), C.c_void_p(stream)), "qpc_step_batch")
 
     def solve_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None, task_weight=None,
-                   contact_geometry=None) -> BatchResult:
+                   contact_geometry=None, task_weight_matrix=None) -> BatchResult:
         """Host numpy buffers in, host numpy buffers out (H2D + kernels + D2H inside the call)."""
         h = self.h
         h.sync_defaults()
         q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
-        tw, cg = _prep_tick_parameters(h, task_weight, contact_geometry)
+        twm = None
+        if task_weight_matrix is None:
+            tw, cg = _prep_tick_parameters(h, task_weight, contact_geometry, B)
+        else:
+            tw, cg, twm = _prep_tick_parameters(h, task_weight, contact_geometry, B, task_weight_matrix)
         res = _alloc_out(h, B)
-        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg), _batch_out(res)
+        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg, task_weight_matrix=twm), _batch_out(res)
         check(self.lib, self.lib.qpc_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo), C.c_int32(HOST_PTRS),
                                                  None), "qpc_solve_batch")
         return res

@@ -103,13 +103,16 @@ class MomentumBasedController:
         return self._dev
 
     def __call__(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None,
-                 check: bool = True, task_weight=None, contact_geometry=None) -> BatchResult:
+                 check: bool = True, task_weight=None, contact_geometry=None, task_weight_matrix=None) -> BatchResult:
         """The control tick for B instances.  `desired` [B, ndes] (task order) overrides the tasks' `setdesired!`
         values; contact arrays [B, ncontacts] override the ContactPoint fields per instance; `task_weight`
         [B, ntasks] and `contact_geometry` [B, ncontacts, 7] = (position, normal, mu) are the reference's
-        Parameter-valued task weights and contact frames (momentum.jl:107-110, contacts.jl:39,53-61)."""
+        Parameter-valued task weights and contact frames (momentum.jl:107-110, contacts.jl:39,53-61);
+        `task_weight_matrix` [B, sum dim^2] are Parameter-valued MATRIX weights (momentum.jl:113-117): the dim x dim
+        matrices (row-major) of the matrix-weighted tasks, concatenated in addtask! order."""
         dev = self.finalize()
-        res = dev.solve_host(q, v, desired, contact_weight, contact_maxnormalforce, task_weight, contact_geometry)
+        res = dev.solve_host(q, v, desired, contact_weight, contact_maxnormalforce, task_weight, contact_geometry,
+                             task_weight_matrix)
         if check:
             checkstatus(res.status)
         return res

@@ -18,7 +18,8 @@ struct DeviceBuffers {
   double *q = nullptr, *v = nullptr, *desired = nullptr, *cw = nullptr, *cm = nullptr, *tw = nullptr, *cg = nullptr;
   double *tau = nullptr, *vdot = nullptr, *wrench = nullptr, *res = nullptr;
   int *status = nullptr, *iters = nullptr;
-  long long capB = 0, cap_desired = 0, cap_contact = 0, cap_tw = 0, cap_cg = 0;
+  double* twm = nullptr;  // staging of per-tick matrix weights
+  long long capB = 0, cap_desired = 0, cap_contact = 0, cap_tw = 0, cap_cg = 0, cap_twm = 0;
 };
 struct Backend {
   bool dirty = false;
@@ -284,6 +285,7 @@ static int ensure_capacity(qpc_controller* c, long long B, long long dstride, lo
     b.cap_desired = 0;
     b.cap_contact = 0;
     b.cap_tw = 0;
+    b.cap_twm = 0;
     b.cap_cg = 0;
   }
   if (B * twstride > b.cap_tw) {
@@ -502,6 +504,17 @@ static int configure_kernels(const DevProgram& p) {
   return QPC_OK;
 }
 
+// staging buffer of the per-tick matrix weights (QPC_HOST_PTRS); grown outside steady state like the others
+static int ensure_twm(qpc_controller* c, long long B, long long stride) {
+  DeviceBuffers& b = c->be.buf;
+  const long long need = stride ? B * stride : c->prog.nwmat;
+  if (need > b.cap_twm) {
+    CUDA_TRY(grow(b.twm, need));
+    b.cap_twm = need;
+  }
+  return QPC_OK;
+}
+
 static QpBuffers qp_view(const DeviceBuffers& b) {
   QpBuffers q;
   q.P = b.P;
@@ -528,7 +541,7 @@ struct HostXfer {
   const qpc_batch_in* in;
   const qpc_batch_out* out;
   long long dstride, cstride;  // 0 = one broadcast row (copied once, before the fork)
-  long long twstride = 0, cgstride = 0;
+  long long twstride = 0, cgstride = 0, twmstride = 0;
 };
 
 // the tick on device pointers; asynchronous on `stream`
@@ -564,6 +577,9 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
       if (hx->in->task_weight && hx->twstride)
         CUDA_TRY(cudaMemcpyAsync(hb.tw + lo * hx->twstride, hx->in->task_weight + lo * hx->twstride,
                                  sizeof(double) * cnt * hx->twstride, cudaMemcpyHostToDevice, s));
+      if (hx->in->task_weight_matrix && hx->twmstride)
+        CUDA_TRY(cudaMemcpyAsync(hb.twm + lo * hx->twmstride, hx->in->task_weight_matrix + lo * hx->twmstride,
+                                 sizeof(double) * cnt * hx->twmstride, cudaMemcpyHostToDevice, s));
       if (hx->in->contact_geometry && hx->cgstride)
         CUDA_TRY(cudaMemcpyAsync(hb.cg + lo * hx->cgstride, hx->in->contact_geometry + lo * hx->cgstride,
                                  sizeof(double) * cnt * hx->cgstride, cudaMemcpyHostToDevice, s));
@@ -698,7 +714,7 @@ void qpc_controller_destroy(qpc_controller* c) {
     cudaSetDevice(c->be.device);
     DeviceBuffers& b = c->be.buf;
     void* ptrs[] = {b.P, b.qv, b.G, b.lg, b.ug, b.lb, b.ub, b.des, b.x, b.y, b.q, b.v, b.desired, b.cw,
-                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.tw, b.cg, c->be.d_fb_list, c->be.d_fb_count};
+                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.tw, b.cg, b.twm, c->be.d_fb_list, c->be.d_fb_count};
     for (int i = 0; i < 4; i++)
       if (c->be.ev[i]) cudaEventDestroy(c->be.ev[i]);
     for (void* p : ptrs)
@@ -729,6 +745,8 @@ static int check_tick_parameters(const DevProgram& p, const qpc_batch_in* in) {
     return qpc_fail(QPC_ERR_ARG, "task_weight_stride smaller than the number of tasks");
   if (in->contact_geometry && in->contact_geometry_stride != 0 && in->contact_geometry_stride < 7 * p.ncontacts)
     return qpc_fail(QPC_ERR_ARG, "contact_geometry_stride smaller than 7 x the number of contacts");
+  if (in->task_weight_matrix && in->task_weight_matrix_stride != 0 && in->task_weight_matrix_stride < p.nwmat)
+    return qpc_fail(QPC_ERR_ARG, "task_weight_matrix_stride smaller than the matrix-weight storage (sum of dim^2)");
   return QPC_OK;
 }
 // device pointers: use the caller's arrays; host pointers: broadcast rows are copied here, per-instance rows by the
@@ -737,9 +755,20 @@ static int stage_tick_parameters(qpc_controller* c, long long B, const qpc_batch
                                  BatchIO& io, cudaStream_t s) {
   const DevProgram& p = c->prog;
   DeviceBuffers& b = c->be.buf;
-  io.tweight = io.cgeom = nullptr;
-  io.tweight_stride = io.cgeom_stride = 0;
+  io.tweight = io.cgeom = io.twmat = nullptr;
+  io.tweight_stride = io.cgeom_stride = io.twmat_stride = 0;
   if (!in) return QPC_OK;
+  if (in->task_weight_matrix && p.nwmat > 0) {
+    io.twmat_stride = in->task_weight_matrix_stride;
+    io.twmat = in->task_weight_matrix;
+    if (host) {
+      int rc = ensure_twm(c, B, io.twmat_stride);
+      if (rc) return rc;
+      const long long cnt = io.twmat_stride ? (copy_all ? B * io.twmat_stride : 0) : p.nwmat;
+      if (cnt) CUDA_TRY(cudaMemcpyAsync(b.twm, in->task_weight_matrix, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, s));
+      io.twmat = b.twm;
+    }
+  }
   if (in->task_weight) {
     io.tweight_stride = in->task_weight_stride;
     io.tweight = in->task_weight;
@@ -827,7 +856,8 @@ int qpc_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const 
   (void)crows;
   rc = stage_tick_parameters(c, B, in, true, false, io, s);
   if (rc) return rc;
-  HostXfer hx{in, out, dstride, cstride, twstride, cgstride};
+  HostXfer hx{in, out, dstride, cstride, twstride, cgstride,
+              (in->task_weight_matrix && p.nwmat > 0) ? in->task_weight_matrix_stride : 0};
   rc = run_tick(c, B, io, b.tau, b.vdot, b.wrench, b.status, b.iters, b.res, nullptr, s, &hx);
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(s));

@@ -235,6 +235,7 @@ inline std::string compile_program(const HostController& hc, DevProgram& p) {
     row += 6;
   }
   p.mg = row;
+  p.nwmat = nw;
   for (int c = 0; c < p.ncontacts; c++) {
     const HostContact& hcn = hc.contacts[c];
     DevContact& d = p.contacts[c];

@@ -21,6 +21,7 @@ struct KinSmem {
   double *GC;                           // ncontacts * N * 6 world wrench of each unit generator
   double *Jt, *bt;                      // 6 x nv task Jacobian scratch, 16 scalars
   double *tw;                           // QPC_MAXT scalar task weights of this tick
+  const double* wm;                     // matrix weights of this tick (Wbuf layout): the per-tick Parameter or pg->Wbuf
   double *ct;                           // per contact (kin_ct_stride): z_up rotation 9, position 3, B 3N, B'B N^2, maxrho factor
 };
 QPC_HD int kin_ct_stride(int N) { return 13 + 3 * N + N * N; }
@@ -71,6 +72,7 @@ QPC_DEV void kin_load(const DevProgram* __restrict__ pg, const BatchIO& io, long
   }
   for (int i = t; i < pg->ntasks; i += nt)
     s.tw[i] = io.tweight ? io.tweight[inst * io.tweight_stride + i] : pg->tasks[i].weight;
+  s.wm = io.twmat ? io.twmat + inst * io.twmat_stride : pg->Wbuf;
   // contact table of this tick: the setup-time ContactPoint geometry, or the per-tick Parameters (contacts.jl:53-61)
   const int N = pg->N, cts = kin_ct_stride(N);
   for (int c = t; c < pg->ncontacts; c += nt) {
@@ -367,7 +369,7 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
       if (t.mode == 1) {
         for (int k = t0; k < t.dim; k += nt) P[(t.scol0 + k) * n + t.scol0 + k] = 2.0 * s.tw[ti];
       } else {  // e'We with a possibly unsymmetric W: the Hessian is W + W'
-        const double* W = pg->Wbuf + t.w_off;
+        const double* W = s.wm + t.w_off;
         for (int k = t0; k < t.dim * t.dim; k += nt) {
           const int a = k / t.dim, b = k % t.dim;
           P[(t.scol0 + a) * n + t.scol0 + b] = W[a * t.dim + b] + W[b * t.dim + a];

@@ -65,6 +65,7 @@ struct DevProgram {
   DevTask tasks[QPC_MAXT];
   int path_body[QPC_MAXPATH], path_sign[QPC_MAXPATH];
   double Wbuf[QPC_MAXW];
+  int nwmat;  // doubles of Wbuf in use (sum of dim^2 over the matrix-weighted tasks)
   DevContact contacts[QPC_MAXC];
   double def_desired[QPC_MAXDES], def_cweight[QPC_MAXC], def_cmaxnf[QPC_MAXC];
   // ---- StandingController constants (standing.jl:1-16) ---------------------------------------------------------
@@ -83,6 +84,8 @@ struct BatchIO {
   const double* tweight = nullptr;  // [B][tweight_stride] scalar weight of every task, addtask! order (momentum.jl:107-110)
   const double* cgeom = nullptr;    // [B][cgeom_stride] per contact position[3], normal[3], mu (contacts.jl:39,53-61)
   long long tweight_stride = 0, cgeom_stride = 0;
+  const double* twmat = nullptr;    // [B][twmat_stride] matrix weights of the matrix-weighted tasks, Wbuf layout (momentum.jl:113-117)
+  long long twmat_stride = 0;
 };
 
 // the condensed QP of every instance, as written by the assembly kernel and consumed by the ADMM kernel

@@ -259,4 +259,7 @@ int qpc_controller_dims(const qpc_controller* c, int32_t* nq, int32_t* nv, int32
   return QPC_OK;
 }
 
+// doubles of one row of qpc_batch_in.task_weight_matrix: sum of dim^2 over the matrix-weighted tasks (addtask! order)
+int qpc_controller_weight_matrix_doubles(const qpc_controller* c) { return (c && c->finalized) ? c->prog.nwmat : 0; }
+
 }  // extern "C"

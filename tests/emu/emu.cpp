@@ -41,6 +41,8 @@ static BatchIO make_io(const qpc_batch_in* in) {
   io.tweight_stride = in->task_weight_stride;
   io.cgeom = in->contact_geometry;
   io.cgeom_stride = in->contact_geometry_stride;
+  io.twmat = in->task_weight_matrix;
+  io.twmat_stride = in->task_weight_matrix_stride;
   return io;
 }
 

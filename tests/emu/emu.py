@@ -31,13 +31,19 @@ class EmuController:
         self.lib = L.load(build())
         self.h = L.Handles(self.lib, program, 0)
 
-    def solve(self, q, v, desired=None, cw=None, cm=None, task_weight=None, contact_geometry=None):
+    def solve(self, q, v, desired=None, cw=None, cm=None, task_weight=None, contact_geometry=None,
+              task_weight_matrix=None):
         h = self.h
         h.sync_defaults()
         q, v, desired, cw, cm, B = L._prep_host_inputs(h, q, v, desired, cw, cm)
-        tw, cg = L._prep_tick_parameters(h, task_weight, contact_geometry)
+        twm = None
+        if task_weight_matrix is None:
+            tw, cg = L._prep_tick_parameters(h, task_weight, contact_geometry, B)
+        else:
+            tw, cg, twm = L._prep_tick_parameters(h, task_weight, contact_geometry, B, task_weight_matrix)
         res = L._alloc_out(h, B)
-        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg), L._batch_out(res)
+        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg,
+                            task_weight_matrix=twm), L._batch_out(res)
         L.check(self.lib, self.lib.emu_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo)), "emu_solve_batch")
         return res
 

@@ -99,3 +99,68 @@ def test_gpu_matches_oracle_with_per_tick_parameters(orc):
     res_b = ctrl.lowlevel(q, v, task_weight=tw[0], contact_geometry=cg[0])
     res_r = ctrl.lowlevel(q, v, task_weight=np.tile(tw[0], (96, 1)), contact_geometry=np.tile(cg[0], (96, 1, 1)))
     assert np.array_equal(res_b.tau, res_r.tau)
+
+
+# ---- Parameter-valued MATRIX weights (momentum.jl:113-117; test/controller.jl:232-285 modes 4 and 5) -----------------------
+def _matrix_weight_setup(seed=31):
+    from qpcontrol_jl_b200 import MomentumBasedController, SpatialAccelerationTask, LinearMomentumRateTask
+    from qpcontrol_jl_b200.mechanism import rand_floating_humanoid
+    rng = np.random.default_rng(seed)
+    mech = rand_floating_humanoid(rng)
+    B = 6
+    q = np.stack([mech.rand_configuration(rng) for _ in range(B)])
+    v = 0.3 * rng.standard_normal((B, mech.nv))
+    W6 = rng.random((B, 6, 6))
+    W6 = W6 @ W6.transpose(0, 2, 1) + np.eye(6)
+    W3 = rng.random((B, 3, 3))            # deliberately unsymmetric: the Hessian block is W + W'
+    W3 = W3 + 2.0 * np.eye(3)
+
+    def build(Wa, Wb):
+        ctrl = MomentumBasedController(mech, OSQPSettings.test_suite(), floatingjoint=0)
+        t1 = SpatialAccelerationTask(mech, mech.findbody("r_hand"), mech.findbody("l_foot"), frame=mech.findbody("r_hand"))
+        t2 = LinearMomentumRateTask(mech)
+        ctrl.addtask(t1, Wa)
+        ctrl.addtask(t2, Wb)
+        for j in range(mech.nb):
+            ctrl.regularize(j, 0.1)
+        t1.setdesired(np.linspace(-0.3, 0.4, 6))
+        t2.setdesired(mech.total_mass * mech.gravity * 0.0 + np.array([1.0, -2.0, 0.5]))
+        return ctrl
+    return mech, q, v, W6, W3, build
+
+
+def _check_matrix_parameters(solve_of):
+    mech, q, v, W6, W3, build = _matrix_weight_setup()
+    B = len(q)
+    # one controller whose setup-time matrices are placeholders, driven by per-tick matrices ...
+    ctrl = build(np.eye(6), np.eye(3))
+    twm = np.concatenate([W6.reshape(B, 36), W3.reshape(B, 9)], axis=1)
+    res = solve_of(ctrl)(q, v, task_weight_matrix=twm)
+    assert np.all(res.status == 1)
+    # ... must equal, instance by instance, controllers BUILT with those matrices
+    for i in range(B):
+        ref = solve_of(build(W6[i], W3[i]))(q[i:i + 1], v[i:i + 1])
+        assert ref.status[0] == 1
+        np.testing.assert_allclose(res.vdot[i], ref.vdot[0], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(res.tau[i], ref.tau[0], rtol=0, atol=1e-7)
+    # a broadcast row = the same matrices for every instance
+    one = solve_of(ctrl)(q, v, task_weight_matrix=twm[0])
+    np.testing.assert_allclose(one.vdot[0], res.vdot[0], rtol=0, atol=1e-12)
+    # and the placeholder matrices give a different answer (the Parameter is really read)
+    plain = solve_of(ctrl)(q, v)
+    assert np.abs(plain.vdot - res.vdot).max() > 1e-4
+    # shape validation: rows must match the batch
+    with pytest.raises(ValueError):
+        solve_of(ctrl)(q, v, task_weight_matrix=twm[:3])
+    with pytest.raises(ValueError):
+        solve_of(ctrl)(q, v, task_weight_matrix=twm[:, :40])
+
+
+def test_matrix_weight_parameters_emulation():
+    from emu import emu
+    _check_matrix_parameters(lambda ctrl: (lambda q, v, **kw: emu.EmuController(ctrl.program).solve(q, v, **kw)))
+
+
+@pytest.mark.gpu
+def test_matrix_weight_parameters_gpu():
+    _check_matrix_parameters(lambda ctrl: (lambda q, v, **kw: ctrl(q, v, check=False, **kw)))
