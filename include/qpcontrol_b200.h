@@ -70,8 +70,12 @@ typedef struct {
 
 /* solve_batch flags */
 enum {
-  QPC_HOST_PTRS = 0,   /* all batch pointers are host memory: the library stages through pinned buffers, copies H2D,
-                          runs, copies D2H and synchronises before returning */
+  QPC_HOST_PTRS = 0,   /* all batch pointers are host memory: the library copies H2D into its device staging buffers
+                          (chunk by chunk, each chunk's copies on that chunk's stream), runs, copies D2H and synchronises
+                          before returning.  Page-locked caller buffers (qpc_pin_host_buffer, or memory that already is
+                          pinned) make those copies asynchronous DMA that overlaps the other chunks' kernels; PAGEABLE
+                          buffers (a plain Julia Matrix{Float64}) are accepted -- the CUDA driver then stages them and
+                          each copy blocks the calling thread, so the PCIe time is no longer hidden */
   QPC_DEVICE_PTRS = 1  /* all batch pointers are device memory on the controller's device: fully asynchronous on
                           `stream` */
 };
@@ -163,6 +167,15 @@ int qpc_controller_weight_matrix_doubles(const qpc_controller*);
 /* ---- the control tick for B instances: (controller)(tau, t, x) (momentum.jl:41-81 / standing.jl:58-89) ------------ */
 int qpc_solve_batch(qpc_controller*, int64_t B, const qpc_batch_in*, const qpc_batch_out*, int32_t flags,
                     void* stream /* cudaStream_t, QPC_DEVICE_PTRS only; NULL = default stream */);
+/* The same tick for one batch spread over several devices from ONE process (SURVEY.md 8(b) threading row, 8(e)): `ctrls`
+ * are replicas of one program finalized on different devices (qpc_finalize(ctrl_k, device_k)); the batch is cut into
+ * nctrl contiguous shards (the first B % nctrl shards one instance longer), one host thread per controller runs
+ * qpc_solve_batch(QPC_HOST_PTRS) on its shard, nothing is exchanged between devices.  Results do not depend on nctrl. */
+int qpc_solve_batch_multi(qpc_controller* const* ctrls, int32_t nctrl, int64_t B, const qpc_batch_in*,
+                          const qpc_batch_out*);
+/* page-lock / release a caller-owned host buffer used with QPC_HOST_PTRS (see the flag's description) */
+int qpc_pin_host_buffer(void* ptr, int64_t bytes);
+int qpc_unpin_host_buffer(void* ptr);
 /* ensure workspaces for batches up to B exist (no allocation happens inside qpc_solve_batch afterwards) */
 int qpc_reserve(qpc_controller*, int64_t B);
 /* number of kernels launched by this controller so far */

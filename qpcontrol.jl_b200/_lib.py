@@ -64,7 +64,8 @@ SETUP_SYMBOLS = ["qpc_version", "qpc_last_error", "qpc_device_count", "qpc_defau
 COMPUTE_SYMBOLS = ["qpc_solve_batch", "qpc_reserve", "qpc_launch_count", "qpc_assemble_batch", "qpc_solve_qp_batch",
                    "qpc_set_profiling", "qpc_stage_times", "qpc_measure_fp64_peak", "qpc_set_warm_start",
                    "qpc_reset_warm_start", "qpc_step_batch", "qpc_set_admm_elimination", "qpc_admm_eliminated",
-                   "qpc_set_admm_warp", "qpc_admm_warp"]
+                   "qpc_set_admm_warp", "qpc_admm_warp", "qpc_solve_batch_multi", "qpc_pin_host_buffer",
+                   "qpc_unpin_host_buffer"]
 
 _libs = {}
 
@@ -272,6 +273,34 @@ def _batch_out(res: BatchResult, ptr=lambda a: a.ctypes.data):
     return bo
 
 
+def solve_host_multi(devs, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None, task_weight=None,
+                     contact_geometry=None) -> BatchResult:
+    """One batch over several devices from this process (qpc_solve_batch_multi): `devs` are DeviceControllers of replicas
+    of one program, finalized on different devices; contiguous shards, one host thread per device inside the library."""
+    h = devs[0].h
+    for d in devs:
+        d.h.sync_defaults()
+    q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
+    tw, cg = _prep_tick_parameters(h, task_weight, contact_geometry, B)
+    res = _alloc_out(h, B)
+    bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg), _batch_out(res)
+    arr = (C.c_void_p * len(devs))(*[d.h.ctrl for d in devs])
+    check(devs[0].lib, devs[0].lib.qpc_solve_batch_multi(arr, C.c_int32(len(devs)), C.c_int64(B), C.byref(bi), C.byref(bo)),
+          "qpc_solve_batch_multi")
+    return res
+
+
+def pin_host_buffer(a: np.ndarray):
+    """Page-lock a numpy array used as a QPC_HOST_PTRS buffer (qpc_pin_host_buffer); unpin before it is freed."""
+    lib = load()
+    check(lib, lib.qpc_pin_host_buffer(C.c_void_p(a.ctypes.data), C.c_int64(a.nbytes)), "qpc_pin_host_buffer")
+
+
+def unpin_host_buffer(a: np.ndarray):
+    lib = load()
+    check(lib, lib.qpc_unpin_host_buffer(C.c_void_p(a.ctypes.data)), "qpc_unpin_host_buffer")
+
+
 class DeviceController:
     """The CUDA controller behind `MomentumBasedController.finalize()`."""
 
@@ -449,3 +478,16 @@ def solve_qp_batch_host(P, qv, G, lg, ug, lb=None, ub=None, settings: Optional[O
                                       _p(out["y"]), _p(out["status"]), _p(out["iters"]), _p(out["res"]),
                                       C.c_int32(HOST_PTRS), None), "qpc_solve_qp_batch")
     return out
+
+
+def solve_qp_batch_device(B, n, mg, nbox, P, qv, G, lg, ug, lb, ub, settings: Optional[OSQPSettings], x, y, status, iters,
+                          residuals, device: int = 0, stream: int = 0):
+    """Raw batched dense QPs through qpc_solve_qp_batch with DEVICE buffers (objects with .data_ptr(), e.g. torch
+    tensors): asynchronous on `stream`, no host copies."""
+    lib = load()
+    st = qpc_settings.from_py(settings or OSQPSettings())
+    dp = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    check(lib, lib.qpc_solve_qp_batch(C.c_int32(device), C.c_int64(B), C.c_int32(n), C.c_int32(mg), C.c_int32(nbox),
+                                      dp(P), dp(qv), dp(G), dp(lg), dp(ug), dp(lb), dp(ub), C.byref(st), dp(x), dp(y),
+                                      dp(status), dp(iters), dp(residuals), C.c_int32(DEVICE_PTRS),
+                                      C.c_void_p(stream) if stream else None), "qpc_solve_qp_batch")

@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 struct DeviceBuffers {
@@ -323,6 +325,22 @@ static int admm_grid(const QpBuffers& qb, long long base, long long B) {
   return (qb.list && qb.list_grid > 0 && qb.list_grid < g) ? qb.list_grid : g;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and per device, not per controller: it is only ever RAISED
+// (per-device high-water mark), so that finalising a controller with a smaller mechanism cannot break the launches of an
+// earlier, larger one on the same device
+static std::mutex g_attr_mu;
+template <class K>
+static cudaError_t raise_dyn_smem(K kernel, int bytes, int (&mark)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  std::lock_guard<std::mutex> lock(g_attr_mu);
+  if (bytes <= mark[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) mark[dev] = bytes;
+  return e;
+}
+static int g_mark_asm[64], g_mark_id[64], g_mark_admm128[64], g_mark_admm512[64], g_mark_kinwarp[64];
 // ---- ADMM dispatch: register-resident kernel when the KKT matrix fits the register file, shared-memory kernel otherwise
 // returns a code TC * 100 + NB, or 0 for the shared-memory kernel
 static int reg_tile(int NK) {
@@ -371,6 +389,33 @@ static cudaError_t launch_reg(const Settings& st, const QpBuffers& qb, int n, in
   }
   return le;
 }
+// Global scratch of the matrices-in-L2 fallback (QPs whose matrices exceed shared memory).  One buffer per device, shared
+// by every caller on that device and kept (it only grows, outside steady state: no allocation once a size has been seen).
+// Launches that use it are serialised on the buffer through an event -- wait before, record after, both under the mutex
+// -- so two streams never work in it at once.
+template <class Launch>
+static cudaError_t with_admm_global_scratch(int dev, size_t doubles, cudaStream_t stream, Launch launch) {
+  static std::mutex mu;
+  static double* buf[64] = {nullptr};
+  static size_t cap[64] = {0};
+  static cudaEvent_t last[64] = {nullptr};
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(mu);
+  cudaError_t e;
+  if (!last[dev] && (e = cudaEventCreateWithFlags(&last[dev], cudaEventDisableTiming)) != cudaSuccess) return e;
+  if (doubles > cap[dev]) {
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+    if (buf[dev]) cudaFree(buf[dev]);
+    buf[dev] = nullptr;
+    cap[dev] = 0;
+    if ((e = cudaMalloc((void**)&buf[dev], sizeof(double) * doubles)) != cudaSuccess) return e;
+    cap[dev] = doubles;
+  } else if ((e = cudaStreamWaitEvent(stream, last[dev], 0)) != cudaSuccess) {
+    return e;
+  }
+  if ((e = launch(buf[dev])) != cudaSuccess) return e;
+  return cudaEventRecord(last[dev], stream);
+}
 // returns cudaSuccess or the launch error; `smem_configured` = the v1 kernel's attribute was already set for this size
 // instances [base, B)
 static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, int mg, int nbx, long long base,
@@ -407,7 +452,7 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
     return cudaGetLastError();
   }
   if (asmem <= 227 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(qpc_admm_kernel<ADMM_BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem);
+    cudaError_t e = raise_dyn_smem(qpc_admm_kernel<ADMM_BIG_THREADS>, asmem, g_mark_admm512);
     if (e != cudaSuccess) return e;
     qpc_admm_kernel<ADMM_BIG_THREADS><<<admm_grid(qb, base, B), ADMM_BIG_THREADS, asmem, stream>>>(st, qb, n, mg, nbx, base, B, nullptr);
     return cudaGetLastError();
@@ -420,16 +465,12 @@ static cudaError_t launch_admm(const Settings& st, const QpBuffers& qb, int n, i
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long grid = B - base < 2ll * sms ? B - base : 2ll * sms;
-  double* scratch = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&scratch, sizeof(double) * (size_t)grid * admm_matrix_doubles(n, mg), stream);
+  cudaError_t e = raise_dyn_smem(qpc_admm_kernel<ADMM_BIG_THREADS>, vsmem, g_mark_admm512);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(qpc_admm_kernel<ADMM_BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, vsmem);
-  if (e == cudaSuccess) {
+  return with_admm_global_scratch(dev, (size_t)grid * admm_matrix_doubles(n, mg), stream, [&](double* scratch) {
     qpc_admm_kernel<ADMM_BIG_THREADS><<<(int)grid, ADMM_BIG_THREADS, vsmem, stream>>>(st, qb, n, mg, nbx, base, B, scratch);
-    e = cudaGetLastError();
-  }
-  cudaFreeAsync(scratch, stream);
-  return e;
+    return cudaGetLastError();
+  });
 }
 
 // ---- one-warp-per-QP ADMM (admm_warp.cuh): programs whose unboxed variables are determined by the equality rows ----------
@@ -496,11 +537,18 @@ static int configure_kernels(const DevProgram& p) {
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
   const int asmem = admm_smem_doubles(p.n, p.mg, p.nbx) * 8;
   if (ksm > 227 * 1024) return qpc_fail(QPC_ERR_LIMIT, "mechanism does not fit the 227 KB shared memory of one CTA");
-  CUDA_TRY(cudaFuncSetAttribute(qpc_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
-  CUDA_TRY(cudaFuncSetAttribute(qpc_inverse_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm));
-  if (kin_warp_per_instance(p, ksm)) CUDA_TRY(kin_warp_configure(ksm));
-  if (asmem <= ADMM_BIG_SMEM)
-    CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel<ADMM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
+  CUDA_TRY(raise_dyn_smem(qpc_assemble_kernel, ksm, g_mark_asm));
+  CUDA_TRY(raise_dyn_smem(qpc_inverse_dynamics_kernel, ksm, g_mark_id));
+  if (kin_warp_per_instance(p, ksm)) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    if (dev < 0 || dev >= 64 || ksm > g_mark_kinwarp[dev]) {
+      CUDA_TRY(kin_warp_configure(ksm));
+      if (dev >= 0 && dev < 64) g_mark_kinwarp[dev] = ksm;
+    }
+  }
+  if (asmem <= ADMM_BIG_SMEM) CUDA_TRY(raise_dyn_smem(qpc_admm_kernel<ADMM_THREADS>, asmem, g_mark_admm128));
   return QPC_OK;
 }
 
@@ -864,6 +912,81 @@ int qpc_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const 
   return QPC_OK;
 }
 
+// ---- single-process multi-GPU entry point: contiguous shards, one host thread per controller / device, no collective -----
+int qpc_solve_batch_multi(qpc_controller* const* ctrls, int32_t nctrl, int64_t B, const qpc_batch_in* in,
+                          const qpc_batch_out* out) {
+  if (!ctrls || nctrl < 1 || !in || !out || !in->q || !in->v || B < 0)
+    return qpc_fail(QPC_ERR_ARG, "qpc_solve_batch_multi: bad arguments");
+  for (int k = 0; k < nctrl; k++) {
+    if (!ctrls[k] || !ctrls[k]->finalized) return qpc_fail(QPC_ERR_STATE, "qpc_solve_batch_multi: controller not finalized");
+    const DevProgram &a = ctrls[0]->prog, &b = ctrls[k]->prog;
+    if (a.nq != b.nq || a.nv != b.nv || a.ndes != b.ndes || a.ncontacts != b.ncontacts || a.ntasks != b.ntasks ||
+        a.n != b.n || a.mg != b.mg || a.nbx != b.nbx || a.nwmat != b.nwmat)
+      return qpc_fail(QPC_ERR_ARG, "qpc_solve_batch_multi: the controllers must be replicas of one program");
+    for (int j = 0; j < k; j++)
+      if (ctrls[j] == ctrls[k]) return qpc_fail(QPC_ERR_ARG, "qpc_solve_batch_multi: a controller handle appears twice");
+  }
+  if (B == 0) return QPC_OK;
+  const DevProgram& p = ctrls[0]->prog;
+  std::vector<int> rc(nctrl, QPC_OK);
+  std::vector<std::string> msg(nctrl);
+  std::vector<std::thread> th;
+  auto shard = [&](int k) {
+    const long long base = B / nctrl, extra = B % nctrl;
+    const long long lo = k * base + (k < extra ? k : extra), cnt = base + (k < extra ? 1 : 0);
+    if (cnt == 0) return;
+    qpc_batch_in i2 = *in;
+    qpc_batch_out o2 = *out;
+    i2.q += lo * p.nq;
+    i2.v += lo * p.nv;
+    if (i2.desired) i2.desired += lo * i2.desired_stride;
+    if (i2.contact_weight) i2.contact_weight += lo * i2.contact_stride;
+    if (i2.contact_maxnormalforce) i2.contact_maxnormalforce += lo * i2.contact_stride;
+    if (i2.task_weight) i2.task_weight += lo * i2.task_weight_stride;
+    if (i2.contact_geometry) i2.contact_geometry += lo * i2.contact_geometry_stride;
+    if (i2.task_weight_matrix) i2.task_weight_matrix += lo * i2.task_weight_matrix_stride;
+    if (o2.tau) o2.tau += lo * p.nv;
+    if (o2.vdot) o2.vdot += lo * p.nv;
+    if (o2.wrench) o2.wrench += lo * p.ncontacts * 6;
+    if (o2.status) o2.status += lo;
+    if (o2.iters) o2.iters += lo;
+    if (o2.residuals) o2.residuals += 2 * lo;
+    if (o2.factorizations) o2.factorizations += lo;
+    rc[k] = qpc_solve_batch(ctrls[k], cnt, &i2, &o2, QPC_HOST_PTRS, nullptr);
+    if (rc[k] != QPC_OK) msg[k] = qpc_last_error();  // the error string is thread-local: carry it to the caller's thread
+  };
+  for (int k = 1; k < nctrl; k++) th.emplace_back(shard, k);
+  shard(0);
+  for (auto& t : th) t.join();
+  for (int k = 0; k < nctrl; k++)
+    if (rc[k] != QPC_OK) return qpc_fail(rc[k], "qpc_solve_batch_multi: shard " + std::to_string(k) + ": " + msg[k]);
+  return QPC_OK;
+}
+
+// Page-locks a caller-owned host buffer (cudaHostRegister, portable across devices) so that the QPC_HOST_PTRS copies are
+// asynchronous DMA transfers that overlap the kernels of other chunks; pageable buffers work too, the driver then stages
+// them and every copy blocks the calling thread.  The caller unpins before freeing the buffer.
+int qpc_pin_host_buffer(void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return qpc_fail(QPC_ERR_ARG, "qpc_pin_host_buffer: bad arguments");
+  cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    return QPC_OK;
+  }
+  CUDA_TRY(e);
+  return QPC_OK;
+}
+int qpc_unpin_host_buffer(void* ptr) {
+  if (!ptr) return qpc_fail(QPC_ERR_ARG, "qpc_unpin_host_buffer: null pointer");
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e == cudaErrorHostMemoryNotRegistered) {
+    cudaGetLastError();
+    return QPC_OK;
+  }
+  CUDA_TRY(e);
+  return QPC_OK;
+}
+
 int qpc_set_warm_start(qpc_controller* c, int32_t on) {
   if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
   std::lock_guard<std::mutex> lock(c->be.mu);
@@ -1212,8 +1335,7 @@ int qpc_solve_qp_batch(int32_t device, int64_t B, int32_t n, int32_t mg, int32_t
   if (admm_vector_doubles(n, mg, nbox) * 8 > 227 * 1024)
     return qpc_fail(QPC_ERR_LIMIT, "QP vectors do not fit the 227 KB shared memory of one CTA");
   CUDA_TRY(cudaSetDevice(device));
-  if (asmem <= ADMM_BIG_SMEM)
-    CUDA_TRY(cudaFuncSetAttribute(qpc_admm_kernel<ADMM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, asmem));
+  if (asmem <= ADMM_BIG_SMEM) CUDA_TRY(raise_dyn_smem(qpc_admm_kernel<ADMM_THREADS>, asmem, g_mark_admm128));
   QpBuffers qb;
   qb = QpBuffers();
   if (flags == QPC_DEVICE_PTRS) {

@@ -2,6 +2,7 @@
 // the host.  Included by api.cu (CUDA backend) and by tests/emu/emu.cpp (CPU emulation of the kernel bodies, test
 // infrastructure); each defines `struct Backend` before including this file.
 #pragma once
+#include <mutex>
 #include <cstdio>
 #include <string>
 
@@ -148,6 +149,9 @@ int qpc_add_contact(qpc_controller* c, int32_t body, const double position[3], c
 
 int qpc_set_contact_params(qpc_controller* c, int32_t contact, double weight, double maxnormalforce) {
   if (!c || contact < 0 || contact >= (int)c->hc.contacts.size()) return qpc_fail(QPC_ERR_ARG, "bad contact index");
+  // post-finalize setters mutate the program a concurrent qpc_solve_batch uploads: same mutex as the tick
+  std::unique_lock<std::mutex> lock(c->be.mu, std::defer_lock);
+  if (c->finalized) lock.lock();
   c->hc.contacts[contact].weight = weight;
   c->hc.contacts[contact].maxnf = maxnormalforce;
   if (c->finalized) {
@@ -191,6 +195,9 @@ int qpc_add_task(qpc_controller* c, int32_t kind, int32_t source_body, int32_t t
 
 int qpc_set_task_desired(qpc_controller* c, int32_t task, const double* desired) {
   if (!c || task < 0 || task >= (int)c->hc.tasks.size()) return qpc_fail(QPC_ERR_ARG, "bad task index");
+  if (!desired) return qpc_fail(QPC_ERR_ARG, "qpc_set_task_desired: null desired");
+  std::unique_lock<std::mutex> lock(c->be.mu, std::defer_lock);
+  if (c->finalized) lock.lock();
   qpc::HostTask& t = c->hc.tasks[task];
   t.desired.assign(desired, desired + t.dim);
   if (c->finalized) {
@@ -218,6 +225,21 @@ int qpc_standing_setup(qpc_controller* c, int32_t linmom_task, int32_t pelvis_ta
     return qpc_fail(QPC_ERR_ARG, "qpc_standing_setup: bad task indices");
   if (c->hc.tasks[linmom_task].kind != QPC_TASK_LINEAR_MOMENTUM_RATE || c->hc.tasks[pelvis_task].kind != QPC_TASK_ANGULAR)
     return qpc_fail(QPC_ERR_ARG, "qpc_standing_setup: task kinds do not match the standing controller");
+  {
+    // every index the program compiler later dereferences is checked here (standing.jl:46-49: one 1-dof
+    // JointAccelerationTask per position-controlled joint)
+    const qpc::HostMechanism& m = *c->hc.mech;
+    if (njoints < 0 || (njoints > 0 && (!joint_tasks || !joints || !kp || !kd || !qref)) || !comref)
+      return qpc_fail(QPC_ERR_ARG, "qpc_standing_setup: bad joint arrays");
+    if (pelvis_body < 0 || pelvis_body >= m.nb) return qpc_fail(QPC_ERR_ARG, "qpc_standing_setup: pelvis body out of range");
+    for (int i = 0; i < njoints; i++) {
+      if (joint_tasks[i] < 0 || joint_tasks[i] >= nt || joints[i] < 0 || joints[i] >= m.nb)
+        return qpc_fail(QPC_ERR_ARG, "qpc_standing_setup: joint / joint task index out of range");
+      const qpc::HostTask& jt = c->hc.tasks[joint_tasks[i]];
+      if (jt.kind != QPC_TASK_JOINT || jt.dim != 1 || jt.joint != joints[i] || m.nvj[joints[i]] != 1)
+        return qpc_fail(QPC_ERR_ARG, "qpc_standing_setup: joint tasks must be 1-dof JointAccelerationTasks of the listed joints");
+    }
+  }
   qpc::HostStanding& s = c->hc.standing;
   s.enabled = true;
   s.linmom_task = linmom_task;
@@ -238,6 +260,8 @@ int qpc_standing_setup(qpc_controller* c, int32_t linmom_task, int32_t pelvis_ta
 
 int qpc_set_settings(qpc_controller* c, const qpc_settings* s) {
   if (!c || !s) return qpc_fail(QPC_ERR_ARG, "null argument");
+  std::unique_lock<std::mutex> lock(c->be.mu, std::defer_lock);
+  if (c->finalized) lock.lock();
   qpc_copy_settings(s, c->hc.settings);
   if (c->finalized) {
     c->prog.settings = c->hc.settings;

@@ -6,8 +6,10 @@
 
 #include <vector>
 
+#include <mutex>
 struct Backend {
   bool dirty = false;
+  std::mutex mu;
 };
 #include "../../qpcontrol.jl_b200/csrc/setup_api.h"
 #include "../../qpcontrol.jl_b200/csrc/admm.cuh"

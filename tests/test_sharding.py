@@ -41,7 +41,7 @@ def _free_port():
 def _worker(rank, world, port, B, out_dir):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
-    from oracle import oracle as orc
+    from emu import emu
     from qpcontrol_jl_b200 import sharding as sh
     sh.init_process_group("gloo")
     assert sh.env_rank_world() == (rank, world, rank)
@@ -49,15 +49,18 @@ def _worker(rank, world, port, B, out_dir):
     q, v = scenarios.atlas_random_states(mech, qnom, B, seed=11)
     lo, hi = sh.shard_range(B, rank, world)
     sh.barrier()
-    ref = orc.OracleController(low.program).solve_batch(q[lo:hi], v[lo:hi])
-    tmax = sh.max_over_ranks([float(rank + 1), ref["seconds"]])
+    # the PRODUCT path's kernel bodies (kin.cuh assembly / inverse dynamics, admm_warp.cuh on CPU fibres), not the oracle
+    res = emu.EmuController(low.program).solve_warp(q[lo:hi], v[lo:hi])
+    tmax = sh.max_over_ranks([float(rank + 1), 0.5])
     assert tmax[0] == float(world)
-    tau = sh.gather_rows(ref["tau"], B)
+    tau = sh.gather_rows(res.tau, B)
     if rank == 0:
         np.save(os.path.join(out_dir, "tau.npy"), tau)
     else:
         assert tau is None
     sh.barrier()
+    import torch.distributed as dist
+    dist.destroy_process_group()  # gloo's background threads must be torn down before the interpreter exits
 
 
 def test_world_size_two_gloo_matches_unsharded(orc, tmp_path):
@@ -67,5 +70,6 @@ def test_world_size_two_gloo_matches_unsharded(orc, tmp_path):
     tau = np.load(tmp_path / "tau.npy")
     mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
     q, v = scenarios.atlas_random_states(mech, qnom, B, seed=11)
-    whole = orc.OracleController(low.program).solve_batch(q, v)
-    assert np.array_equal(tau, whole["tau"])
+    from emu import emu
+    whole = emu.EmuController(low.program).solve_warp(q, v)
+    assert np.array_equal(tau, whole.tau)  # bit-identical: the result of an instance does not depend on its shard
