@@ -197,8 +197,11 @@ function addcontact!(c::MomentumBasedController{N}, body::RigidBody, position::P
     p
 end
 
-# lazy initialize! (momentum.jl:43-46,150-156): pushes the mutable defaults and freezes the program on the device
-function initialize!(c::MomentumBasedController)
+# The reference re-evaluates every Parameter on each `solve!` (tasks.jl:40 `desired`, contacts.jl:54-57 `weight[]`,
+# `maxnormalforce[]`, `disable!`), so `setdesired!` / `disable!` / weight changes made BETWEEN ticks must reach the device:
+# syncdefaults! pushes the current values before every tick (a few dozen setter calls; the library uploads the program
+# once, at the next tick, only if something changed).
+function syncdefaults!(c::MomentumBasedController)
     for p in c.contacts
         check(ccall((:qpc_set_contact_params, LIB[]), Cint, (Ptr{Cvoid}, Int32, Cdouble, Cdouble), c.handle, p.index,
                     p.weight[], p.maxnormalforce[]), "qpc_set_contact_params")
@@ -207,6 +210,11 @@ function initialize!(c::MomentumBasedController)
         check(ccall((:qpc_set_task_desired, LIB[]), Cint, (Ptr{Cvoid}, Int32, Ptr{Cdouble}), c.handle, t.index,
                     t.desired), "qpc_set_task_desired")
     end
+end
+
+# lazy initialize! (momentum.jl:43-46,150-156): pushes the mutable defaults and freezes the program on the device
+function initialize!(c::MomentumBasedController)
+    syncdefaults!(c)
     check(ccall((:qpc_finalize, LIB[]), Cint, (Ptr{Cvoid}, Int32), c.handle, c.device), "qpc_finalize")
     c.initialized = true
 end
@@ -216,9 +224,12 @@ struct qpc_batch_in
     contact_weight::Ptr{Cdouble}; contact_maxnormalforce::Ptr{Cdouble}; contact_stride::Int64
     task_weight::Ptr{Cdouble}; task_weight_stride::Int64            # per-tick Parameter weights (momentum.jl:107-110)
     contact_geometry::Ptr{Cdouble}; contact_geometry_stride::Int64  # per-tick position / normal / mu (contacts.jl:39)
+    task_weight_matrix::Ptr{Cdouble}; task_weight_matrix_stride::Int64  # per-tick matrix weights (momentum.jl:113-117)
 end
 qpc_batch_in(q, v, desired, dstride, cw, cm, cstride) =
-    qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, C_NULL, 0, C_NULL, 0)
+    qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, C_NULL, 0, C_NULL, 0, C_NULL, 0)
+qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, tw, twstride, cg, cgstride) =
+    qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, tw, twstride, cg, cgstride, C_NULL, 0)
 struct qpc_batch_out
     tau::Ptr{Cdouble}; vdot::Ptr{Cdouble}; wrench::Ptr{Cdouble}; status::Ptr{Int32}; iters::Ptr{Int32}
     residuals::Ptr{Cdouble}; factorizations::Ptr{Int32}
@@ -235,6 +246,7 @@ function (c::MomentumBasedController)(tau::Matrix{Float64}, t::Number, q::Matrix
                                       taskweight::Union{Nothing,Matrix{Float64}}=nothing,
                                       contactgeometry::Union{Nothing,Array{Float64,3}}=nothing, check::Bool=true)
     c.initialized || initialize!(c)
+    syncdefaults!(c)   # setdesired! / disable! / weight changes since the last tick (the reference re-reads them in solve!)
     B = size(q, 2)
     nc = length(c.contacts)
     vdot = similar(v); wrench = zeros(6, nc, B); status = zeros(Int32, B); iters = zeros(Int32, B); res = zeros(2, B)
@@ -271,6 +283,7 @@ resetwarmstart!(c::MomentumBasedController) =
 function simulate!(c::MomentumBasedController, q::Matrix{Float64}, v::Matrix{Float64}, dt::Float64, nsteps::Integer;
                    check::Bool=true)
     c.initialized || initialize!(c)
+    syncdefaults!(c)
     B = size(q, 2)
     nc = length(c.contacts)
     tau = zeros(size(v)); vdot = similar(v); wrench = zeros(6, nc, B); status = zeros(Int32, B)
