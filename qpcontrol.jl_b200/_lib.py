@@ -230,6 +230,22 @@ def _prep_host_inputs(h: Handles, q, v, desired, cw, cm):
     return q, v, desired, cw, cm, B
 
 
+def _require(a, shape, name, dtype=np.float64):
+    """Caller-owned host buffer handed to the C ABI as is: right shape, dtype and C-contiguous, or an error (the library
+    would otherwise read or write out of bounds)."""
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or a.shape != tuple(shape) or not a.flags.c_contiguous:
+        raise ValueError(f"{name} must be a C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}; got "
+                         f"{getattr(a, 'dtype', type(a))} {getattr(a, 'shape', None)}")
+
+
+def _require_dev(t, shape, name, at_least=False):
+    """Device tensor handed to the C ABI: contiguous, and of (at least, for outputs larger than the batch) this shape."""
+    sh = tuple(t.shape)
+    ok = len(sh) == len(shape) and sh[1:] == tuple(shape[1:]) and (sh[0] >= shape[0] if at_least else sh[0] == shape[0])
+    if not ok or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous device tensor of shape {tuple(shape)}; got {sh}")
+
+
 def _check_rows(B, **arrays):
     """Per-instance arrays must have exactly B rows: the C ABI copies B * stride doubles from them (a shorter array would
     be read out of bounds).  `base_ndim` = the number of dimensions of ONE row (a broadcast row has that many)."""
@@ -406,9 +422,22 @@ class DeviceController:
         return res
 
     def solve_host_into(self, q, v, res: BatchResult, contact_weight=None, contact_maxnormalforce=None):
-        """As `solve_host`, writing into caller-owned (e.g. pinned) buffers: no allocation, no marshalling copies."""
+        """As `solve_host`, writing into caller-owned (e.g. pinned) buffers: no allocation, no marshalling copies.
+        The buffers must already be C-contiguous float64 of the right shape (checked, never copied)."""
         h = self.h
+        h.sync_defaults()  # cheap: unchanged values do not re-upload the program
         B = q.shape[0]
+        _require(q, (B, h.nq), "q")
+        _require(v, (B, h.nv), "v")
+        for name, a in (("contact_weight", contact_weight), ("contact_maxnormalforce", contact_maxnormalforce)):
+            if a is not None:
+                _require(a, (B, h.ncontacts) if a.ndim == 2 else (h.ncontacts,), name)
+        _require(res.tau, (B, h.nv), "res.tau")
+        _require(res.vdot, (B, h.nv), "res.vdot")
+        _require(res.wrenches, (B, h.ncontacts, 6), "res.wrenches")
+        _require(res.status, (B,), "res.status", np.int32)
+        _require(res.iters, (B,), "res.iters", np.int32)
+        _require(res.residuals, (B, 2), "res.residuals")
         bi, bo = h.batch_in(q, v, None, contact_weight, contact_maxnormalforce), _batch_out(res)
         check(self.lib, self.lib.qpc_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo), C.c_int32(HOST_PTRS),
                                                  None), "qpc_solve_batch")
@@ -420,6 +449,16 @@ class DeviceController:
         (a raw cudaStream_t value).  `out` maps tau / vdot / wrench / status / iters / residuals to tensors."""
         h = self.h
         ptr = lambda t: t.data_ptr()  # noqa: E731
+        _require_dev(q, (B, h.nq), "q", at_least=True)  # a larger tensor may back a smaller batch: the first B rows are used
+        _require_dev(v, (B, h.nv), "v", at_least=True)
+        for name, t, cols in (("desired", desired, h.ndes), ("contact_weight", contact_weight, h.ncontacts),
+                              ("contact_maxnormalforce", contact_maxnormalforce, h.ncontacts)):
+            if t is not None:
+                _require_dev(t, (B, cols) if t.dim() == 2 else (cols,), name, at_least=t.dim() == 2)
+        for name, shape in (("tau", (B, h.nv)), ("vdot", (B, h.nv)), ("wrench", (B, h.ncontacts, 6)), ("status", (B,)),
+                            ("iters", (B,)), ("residuals", (B, 2)), ("factorizations", (B,))):
+            if out.get(name) is not None:
+                _require_dev(out[name], shape, name, at_least=True)
         bi = qpc_batch_in()
         bi.q, bi.v = ptr(q), ptr(v)
         bi.desired = None if desired is None else ptr(desired)

@@ -152,9 +152,10 @@ int qpc_set_contact_params(qpc_controller* c, int32_t contact, double weight, do
   // post-finalize setters mutate the program a concurrent qpc_solve_batch uploads: same mutex as the tick
   std::unique_lock<std::mutex> lock(c->be.mu, std::defer_lock);
   if (c->finalized) lock.lock();
+  const bool changed = c->hc.contacts[contact].weight != weight || c->hc.contacts[contact].maxnf != maxnormalforce;
   c->hc.contacts[contact].weight = weight;
   c->hc.contacts[contact].maxnf = maxnormalforce;
-  if (c->finalized) {
+  if (c->finalized && changed) {  // re-pushing unchanged values every tick (host mirrors do) costs no program upload
     c->prog.def_cweight[contact] = weight;
     c->prog.def_cmaxnf[contact] = maxnormalforce;
     c->be.dirty = true;
@@ -199,8 +200,10 @@ int qpc_set_task_desired(qpc_controller* c, int32_t task, const double* desired)
   std::unique_lock<std::mutex> lock(c->be.mu, std::defer_lock);
   if (c->finalized) lock.lock();
   qpc::HostTask& t = c->hc.tasks[task];
+  bool changed = (int)t.desired.size() != t.dim;
+  for (int i = 0; i < t.dim && !changed; i++) changed = t.desired[i] != desired[i];
   t.desired.assign(desired, desired + t.dim);
-  if (c->finalized) {
+  if (c->finalized && changed) {
     for (int i = 0; i < t.dim; i++) c->prog.def_desired[t.des_off + i] = desired[i];
     c->be.dirty = true;
   }
