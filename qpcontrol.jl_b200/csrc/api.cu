@@ -16,6 +16,7 @@ struct DeviceBuffers {
   double *P = nullptr, *qv = nullptr, *G = nullptr, *lg = nullptr, *ug = nullptr, *lb = nullptr, *ub = nullptr;
   double *des = nullptr, *x = nullptr, *y = nullptr;
   double* rho = nullptr;  // [capB] rho every slot ended its last accepted solve with (<= 0: none) -- warm start
+  double* ksave = nullptr;  // [capB][kin_save_doubles] kinematic state handed from assembly to inverse dynamics
   // staging for QPC_HOST_PTRS
   double *q = nullptr, *v = nullptr, *desired = nullptr, *cw = nullptr, *cm = nullptr, *tw = nullptr, *cg = nullptr;
   double *tau = nullptr, *vdot = nullptr, *wrench = nullptr, *res = nullptr;
@@ -87,6 +88,7 @@ qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb,
     kin_assemble(pg, s, qb.P + inst * n * n, qb.qv + inst * n, qb.G + inst * mg * n, qb.lg + inst * mg,
                  qb.ug + inst * mg, qb.lb + inst * nbx, qb.ub + inst * nbx);
     for (int i = threadIdx.x; i < pg->ndes; i += blockDim.x) qb.des[inst * pg->ndes + i] = s.des[i];
+    if (qb.ksave) kin_save(pg, s, qb.ksave + inst * kin_save_doubles(pg->nb, pg->nv, pg->ncontacts, pg->N));
     __syncthreads();
   }
 }
@@ -271,6 +273,7 @@ static int ensure_capacity(qpc_controller* c, long long B, long long dstride, lo
     CUDA_TRY(grow(b.x, B * n));
     CUDA_TRY(grow(b.y, B * (mg + nbx)));
     CUDA_TRY(grow(b.rho, B));
+    CUDA_TRY(grow(b.ksave, B * kin_save_doubles(p.nb, p.nv, p.ncontacts, p.N)));
     CUDA_TRY(cudaMemset(b.rho, 0, sizeof(double) * (size_t)B));
     CUDA_TRY(grow(b.q, B * p.nq));
     CUDA_TRY(grow(b.v, B * p.nv));
@@ -340,7 +343,7 @@ static cudaError_t raise_dyn_smem(K kernel, int bytes, int (&mark)[64]) {
   if (e == cudaSuccess) mark[dev] = bytes;
   return e;
 }
-static int g_mark_asm[64], g_mark_id[64], g_mark_admm128[64], g_mark_admm512[64], g_mark_kinwarp[64];
+static int g_mark_asm[64], g_mark_id[64], g_mark_admm128[64], g_mark_admm512[64], g_mark_kinwarp[64], g_mark_idsaved[64];
 // ---- ADMM dispatch: register-resident kernel when the KKT matrix fits the register file, shared-memory kernel otherwise
 // returns a code TC * 100 + NB, or 0 for the shared-memory kernel
 static int reg_tile(int NK) {
@@ -549,6 +552,16 @@ static int configure_kernels(const DevProgram& p) {
     }
   }
   if (asmem <= ADMM_BIG_SMEM) CUDA_TRY(raise_dyn_smem(qpc_admm_kernel<ADMM_THREADS>, asmem, g_mark_admm128));
+  {
+    const int idsm = kin_id_smem_doubles(p.nb, p.nv, p.ndes, p.ncontacts, p.N) * 8;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_attr_mu);
+    if (KIN_ID_WPC * idsm <= 227 * 1024 && (dev < 0 || dev >= 64 || idsm > g_mark_idsaved[dev])) {
+      CUDA_TRY(kin_warp_id_saved_configure(idsm));
+      if (dev >= 0 && dev < 64) g_mark_idsaved[dev] = idsm;
+    }
+  }
   return QPC_OK;
 }
 
@@ -579,6 +592,7 @@ static QpBuffers qp_view(const DeviceBuffers& b) {
   q.iters = b.iters;
   q.res = b.res;
   q.rho = b.rho;
+  q.ksave = b.ksave;
   q.warm = 0;
   return q;
 }
@@ -685,8 +699,16 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
     else
       qpc_trivial_status_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, s>>>(qb.status, qb.iters, qb.res, lo, hi);
     if (timed) cudaEventRecord(c->be.ev[2], s);
-    if (kwarp) CUDA_TRY(kin_warp_inverse_dynamics(dp, io, qb, tau, vdot, wrench, lo, hi, ksm, s));
-    else qpc_inverse_dynamics_kernel<<<grid, ID_THREADS, ksm, s>>>(dp, io, qb, tau, vdot, wrench, lo, hi);
+    // inverse dynamics from the state the assembly kernel saved (QPC_ID_SAVED=0: recompute the forward sweep instead)
+    static const bool id_saved = [] { const char* e = getenv("QPC_ID_SAVED"); return !e || e[0] != '0'; }();
+    const int idsm = kin_id_smem_doubles(p.nb, p.nv, p.ndes, p.ncontacts, p.N) * 8;
+    if (id_saved && qb.ksave && KIN_ID_WPC * idsm <= 227 * 1024) {
+      CUDA_TRY(kin_warp_id_saved(dp, qb, tau, vdot, wrench, lo, hi, idsm, s));
+    } else if (kwarp) {
+      CUDA_TRY(kin_warp_inverse_dynamics(dp, io, qb, tau, vdot, wrench, lo, hi, ksm, s));
+    } else {
+      qpc_inverse_dynamics_kernel<<<grid, ID_THREADS, ksm, s>>>(dp, io, qb, tau, vdot, wrench, lo, hi);
+    }
     if (timed) cudaEventRecord(c->be.ev[3], s);
     c->be.launches += 3;
     if (hx) {  // results of this chunk, device staging -> host
@@ -762,7 +784,7 @@ void qpc_controller_destroy(qpc_controller* c) {
     cudaSetDevice(c->be.device);
     DeviceBuffers& b = c->be.buf;
     void* ptrs[] = {b.P, b.qv, b.G, b.lg, b.ug, b.lb, b.ub, b.des, b.x, b.y, b.q, b.v, b.desired, b.cw,
-                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.tw, b.cg, b.twm, c->be.d_fb_list, c->be.d_fb_count};
+                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.ksave, b.tw, b.cg, b.twm, c->be.d_fb_list, c->be.d_fb_count};
     for (int i = 0; i < 4; i++)
       if (c->be.ev[i]) cudaEventDestroy(c->be.ev[i]);
     for (void* p : ptrs)

@@ -30,7 +30,27 @@ qpc_assemble_warp_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffer
     kin_assemble(pg, s, qb.P + inst * n * n, qb.qv + inst * n, qb.G + inst * mg * n, qb.lg + inst * mg,
                  qb.ug + inst * mg, qb.lb + inst * nbx, qb.ub + inst * nbx);
     for (int i = threadIdx.x; i < pg->ndes; i += blockDim.x) qb.des[inst * pg->ndes + i] = s.des[i];
+    if (qb.ksave) kin_save(pg, s, qb.ksave + inst * kin_save_doubles(pg->nb, pg->nv, pg->ncontacts, pg->N));
     QPC_SYNC();
+  }
+}
+
+// inverse dynamics from the kinematic state the assembly kernel saved (kin.cuh: kin_save / kin_id_load): no forward sweep,
+// half the shared memory, one warp per instance
+__global__ void __launch_bounds__(32 * KIN_ID_WPC, KIN_ID_MIN_CTAS)
+qpc_id_saved_warp_kernel(const DevProgram* __restrict__ pg, QpBuffers qb, double* tau, double* vdot, double* wrench,
+                         long long base, long long B) {
+  extern __shared__ double smem_all[];
+  const int per = kin_id_smem_doubles(pg->nb, pg->nv, pg->ndes, pg->ncontacts, pg->N);
+  double* smem = smem_all + threadIdx.y * per;
+  const int ks = kin_save_doubles(pg->nb, pg->nv, pg->ncontacts, pg->N);
+  for (long long inst = base + (long long)blockIdx.x * blockDim.y + threadIdx.y; inst < B;
+       inst += (long long)gridDim.x * blockDim.y) {
+    KinSmem s = kin_id_layout(smem, pg->nb, pg->nv, pg->ndes, pg->ncontacts, pg->N);
+    kin_id_load(pg, s, qb.ksave + inst * ks, qb.des + inst * pg->ndes);
+    double* tdst = tau ? tau + inst * pg->nv : s.Jt;  // tau is always computed; discard into scratch if unwanted
+    kin_inverse_dynamics(pg, s, qb.x + inst * pg->n, vdot ? vdot + inst * pg->nv : nullptr,
+                         wrench ? wrench + inst * pg->ncontacts * 6 : nullptr, tdst);
   }
 }
 
@@ -51,6 +71,18 @@ qpc_inverse_dynamics_warp_kernel(const DevProgram* __restrict__ pg, BatchIO io, 
     kin_inverse_dynamics(pg, s, qb.x + inst * pg->n, vdot ? vdot + inst * pg->nv : nullptr,
                          wrench ? wrench + inst * pg->ncontacts * 6 : nullptr, tdst);
   }
+}
+
+cudaError_t kin_warp_id_saved_configure(int bytes_per_instance) {
+  return cudaFuncSetAttribute(qpc_id_saved_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              KIN_ID_WPC * bytes_per_instance);
+}
+cudaError_t kin_warp_id_saved(const DevProgram* dp, const QpBuffers& qb, double* tau, double* vdot, double* wrench,
+                              long long lo, long long hi, int bytes_per_instance, cudaStream_t s) {
+  const long long g = (hi - lo + KIN_ID_WPC - 1) / KIN_ID_WPC;
+  qpc_id_saved_warp_kernel<<<(unsigned)(g < (1ll << 30) ? g : (1ll << 30)), dim3(32, KIN_ID_WPC),
+                             KIN_ID_WPC * bytes_per_instance, s>>>(dp, qb, tau, vdot, wrench, lo, hi);
+  return cudaGetLastError();
 }
 
 static unsigned warp_grid(long long count) {
