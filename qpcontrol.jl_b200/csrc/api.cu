@@ -534,6 +534,9 @@ static cudaError_t launch_warp(int shape, const Settings& st, const QpBuffers& q
 // tiny mechanisms run the kinematics kernels one warp per instance (kin_warp.cu)
 static bool kin_warp_per_instance(const DevProgram& p, int ksm) {
   static const bool on = [] { const char* e = getenv("QPC_KIN_WARP"); return !e || e[0] != '0'; }();
+  // QPC_KIN_WARP_BODIES=<n>: development knob, raises the body limit (and lifts the 48 KB limit) of the warp-per-instance form
+  static const int maxb = [] { const char* e = getenv("QPC_KIN_WARP_BODIES"); return e ? atoi(e) : KIN_WARP_MAX_BODIES; }();
+  if (maxb != KIN_WARP_MAX_BODIES) return on && p.nb <= maxb && KIN_WPC * ksm <= 227 * 1024;
   return on && p.nb <= KIN_WARP_MAX_BODIES && KIN_WPC * ksm <= KIN_WARP_MAX_SMEM;
 }
 static int configure_kernels(const DevProgram& p) {
