@@ -40,9 +40,10 @@ constexpr int QPC_WARP_FALLBACK = -99;
 
 struct WarpParams {
   double kappa;   // rho of rows on a bound = kappa rho, interior rows rho / kappa (1 = OSQP's uniform rho)
-  double growth;  // the adaptation schedule is first, first * growth, ...
+  double growth;  // adaptation at first, then every max(first, (growth - 1) x current) iterations
   int first;      // first adaptation iteration
   int check;      // residual check interval
+  int aitken;     // extrapolation of slowly converging solves every this many iterations (0 = off)
 };
 
 #if defined(__CUDACC__)
@@ -87,7 +88,8 @@ struct WarpSolver {
   static constexpr int OFF_B3 = OFF_C + 4 * NA;       // b3 [MEP], padded to 4 (4 NA is even: 16-byte alignment holds)
   static constexpr int OFF_HV = OFF_B3 + ((MEP + 3) & ~3);  // h [32]
   static constexpr int OFF_RHO = OFF_HV + 32;         // rho_i [32]
-  static constexpr int SMEM_DOUBLES = OFF_RHO + 32;
+  static constexpr int OFF_AK = OFF_RHO + 32;         // extrapolation history: z, y at the previous point, their last increments [4][32]
+  static constexpr int SMEM_DOUBLES = OFF_AK + 128;
   static constexpr unsigned FULL = 0xffffffffu;
 
   // warp sum; NOT inlined: ~55 call sites x 25 instructions would otherwise be a fifth of the kernel's code, and the
@@ -590,8 +592,10 @@ struct WarpSolver {
     double ds_last = 1e300;  // last evaluated dual normaliser max(|Px|, |A'y|, |q|)
     double rp_last = -1.0;   // primal residual at the previous adaptation point
     bool refactor = true;
+    int hist = 0;            // extrapolation history: 0 none, 1 a previous point, 2 also a previous increment
     for (;;) {
-      if (refactor) {  // the only call site: the inversion is ~1,400 instructions per inlined copy
+      if (refactor) {
+        hist = 0;  // the only call site: the inversion is ~1,400 instructions per inlined copy
         const bool okf = factor(sm, t, t0, rho_i, a3, b3, lane);
         nfac++;
         refactor = false;
@@ -735,7 +739,10 @@ struct WarpSolver {
       if (done) break;
       if (iter == next_chk) next_chk += chk;
       if (adapt) {
-        next_adapt = (int)fmin(ceil(next_adapt * wp.growth), 2.0e9);
+        // schedule: every `first` iterations early on, then geometric (x growth): solves that need several re-weightings of
+        // their rows get them quickly (they used to sit out the gaps of a x2 schedule: 410 iterations instead of 150),
+        // while the number of refactorisations of a long solve stays logarithmic in its length
+        next_adapt = (int)fmin(fmax(ceil(next_adapt * wp.growth), (double)next_adapt + wp.first), 2.0e9);
         // OSQP's rule without its 1e-10 guards: at tight tolerances (residual / norm ~ 1e-11) they saturate the ratio
         // and stop rho from growing when the primal residual sits on its rounding floor (~ cond(K) eps |x|)
         const double prn = pri_res / (ps + 1e-300), drn = dua_res / (ds + 1e-300);
@@ -757,6 +764,58 @@ struct WarpSolver {
           yr *= rho_i / rnew;  // y is unchanged by a rho update; yr = y / rho follows the new rho
           rho_i = rnew;
           refactor = true;
+        }
+      } else if (wp.aitken > 0 && iter % wp.aitken == 0) {
+        // Extrapolation of slowly converging solves (between adaptations): once the active set has settled the iteration
+        // is affine, s+ = M s + c on s = (z, y); when one real mode dominates, successive increments are parallel,
+        // d_k = r d_{k-1}, and the limit is s + d r / (1 - r) (Aitken); r -> 1 is the dual drift of a wrongly active row.
+        // The step is cut so that no clipped row reaches its release point (y crossing 0) and no interior row leaves
+        // the box: the active set, hence the affine regime, is preserved, and ADMM simply continues from the new point
+        // (it converges from any (z, y) at fixed rho).  The heavy tail of the iteration count -- 1,755 iterations on
+        // the worst of 131,072 Atlas states -- becomes 265; typical solves never get here.
+        double* AK = sm + OFF_AK;
+        const double yv = rho_i * yr;
+        bool jumped = false;
+        if (hist >= 1) {
+          const double dz = z - AK[lane], dyv = yv - AK[32 + lane];
+          if (hist >= 2) {
+            const double pz = AK[64 + lane], py = AK[96 + lane];
+            const double dd = wsum(fma(dz, dz, dyv * dyv)), pp = wsum(fma(pz, pz, py * py)), dp = wsum(fma(dz, pz, dyv * py));
+            if (dd > 0.0 && pp > 0.0) {
+              const double cosv = dp / sqrt(dd * pp), rr = dp / pp;
+              if (cosv > 1.0 - 1e-4 && rr > 0.0 && rr < 1.0 - 1e-12) {
+                double bnd = 1e300;
+                const bool clipped = ((z <= lo) || (z >= up)) && !iseq;
+                if (clipped) {
+                  if (yv * dyv < 0.0) bnd = 0.9 * (-yv / dyv);
+                } else if (!iseq) {
+                  if (dz > 0.0) bnd = 0.9 * (up - z) / dz;
+                  else if (dz < 0.0) bnd = 0.9 * (lo - z) / dz;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) bnd = fmin(bnd, __shfl_xor_sync(FULL, bnd, o));
+                const double gain = fmin(rr / (1.0 - rr), bnd);
+                if (gain >= 1.0) {
+                  double zn = fma(gain, dz, z);
+                  zn = zn < lo ? lo : zn;
+                  z = zn > up ? up : zn;
+                  yr = fma(gain, dyv, yv) / rho_i;
+                  hist = 0;
+                  jumped = true;
+                }
+              }
+            }
+          }
+          if (!jumped) {
+            AK[64 + lane] = dz;
+            AK[96 + lane] = dyv;
+            hist = 2;
+          }
+        }
+        if (!jumped) {
+          AK[lane] = z;
+          AK[32 + lane] = yv;
+          if (hist < 1) hist = 1;
         }
       }
     }

@@ -484,6 +484,47 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
   }
 }
 
+// RNEA core (RigidBodyDynamics.inverse_dynamics!, momentum.jl:75): vd [nv], ext [nb][6] external wrench per body in world
+// frame (overwritten with the joint wrenches), acc [nb][6] scratch.  zero_floating: zero_floating_joint_torques!
+// (momentum.jl:93-97) -- the forward dynamics below needs those rows.
+QPC_DEV void kin_rnea(const DevProgram* __restrict__ pg, KinSmem& s, const double* vd, double* ext, double* acc,
+                      double* tau_out, bool zero_floating) {
+  const int nv = pg->nv, nb = pg->nb;
+  // forward: spatial accelerations with gravity as root acceleration, joint wrench = I a + T x* I T - ext
+  for (int lvl = 0; lvl < pg->nlevels; lvl++) {
+    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
+      const int b = pg->level_body[k], par = pg->parent[b];
+      S6 a = par < 0 ? mk6(mk3(0, 0, 0), -ld3(pg->gravity)) : ld6(acc + 6 * par);
+      for (int c = pg->voff[b]; c < pg->voff[b] + pg->nvj[b]; c++) a = a + vd[c] * ld6(s.SW + 6 * c);
+      a = a + (body_bias(s, b) - body_bias(s, par));
+      st6(acc + 6 * b, a);
+    }
+    QPC_SYNC();
+  }
+  for (int b = QPC_TID; b < nb; b += QPC_NT) {
+    S6 w = newton_euler(si_load(s.IW + 10 * b), ld6(acc + 6 * b), ld6(s.TW + 6 * b)) - ld6(ext + 6 * b);
+    st6(ext + 6 * b, w);
+  }
+  QPC_SYNC();
+  // backward: parents accumulate their children's wrenches, deepest level first
+  for (int lvl = pg->nlevels - 2; lvl >= 0; lvl--) {
+    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
+      const int b = pg->level_body[k];
+      S6 w = ld6(ext + 6 * b);
+      for (int c = pg->child_ptr[b]; c < pg->child_ptr[b + 1]; c++) w = w + ld6(ext + 6 * pg->child_idx[c]);
+      st6(ext + 6 * b, w);
+    }
+    QPC_SYNC();
+  }
+  for (int c = QPC_TID; c < nv; c += QPC_NT) {
+    const int b = pg->vbody[c];
+    double tau = dot(ld6(s.SW + 6 * c), ld6(ext + 6 * b));
+    if (zero_floating && b == pg->floating) tau = 0.0;  // zero_floating_joint_torques! (momentum.jl:93-97)
+    tau_out[c] = tau;
+  }
+  QPC_SYNC();
+}
+
 // ---- epilogue: contact wrenches, inverse dynamics (momentum.jl:62-80) ------------------------------------------------
 // x = condensed solution.  Writes vd (nv), per-contact world wrenches (nc x 6) and tau (nv) to the given slots.
 QPC_DEV void kin_inverse_dynamics(const DevProgram* __restrict__ pg, KinSmem& s, const double* x, double* vd_out,
@@ -516,38 +557,120 @@ QPC_DEV void kin_inverse_dynamics(const DevProgram* __restrict__ pg, KinSmem& s,
     ext[k] = a;
   }
   QPC_SYNC();
-  // forward: spatial accelerations with gravity as root acceleration, joint wrench = I a + T x* I T - ext
-  for (int lvl = 0; lvl < pg->nlevels; lvl++) {
-    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
-      const int b = pg->level_body[k], par = pg->parent[b];
-      S6 a = par < 0 ? mk6(mk3(0, 0, 0), -ld3(pg->gravity)) : ld6(acc + 6 * par);
-      for (int c = pg->voff[b]; c < pg->voff[b] + pg->nvj[b]; c++) a = a + vd[c] * ld6(s.SW + 6 * c);
-      a = a + (body_bias(s, b) - body_bias(s, par));
-      st6(acc + 6 * b, a);
+  kin_rnea(pg, s, vd, ext, acc, tau_out, true);
+}
+
+
+// ---- forward dynamics under a soft ground contact: the plant of the closed loop ---------------------
+// notebooks/Standing controller.ipynb:202-214 runs simulate(state, T, PeriodicController(tau, dt, controller)): the
+// simulator applies the commanded torques to the mechanism and the environment answers with contact forces.  Here:
+//   vd = M(q)^-1 (tau - c(q, v, w_ext)),   M by the composite-rigid-body algorithm, c by RNEA at vd = 0 with the contact
+//   wrenches as external wrenches, the solve by Cholesky in shared memory;
+//   contact: every ContactPoint of the controller against the half-space z >= ground_z, normal force
+//   max(0, -k phi - d phidot) on penetration phi < 0 (spring-damper), tangential force -mu f_n v_t / max(|v_t|, v_eps)
+//   (Coulomb friction regularised below v_eps).
+// Restated from the published algorithms of RigidBodyDynamics.dynamics! / RigidBodySim [dep-memory]; the soft-contact
+// model stands for RigidBodyDynamics.Contact's (Hunt-Crossley normal + viscoelastic Coulomb friction with state), of
+// which it keeps the half-space geometry, the penalty normal force and the friction cone, not the friction state.
+struct ContactModel {
+  double k, d, mu, v_eps, ground_z;
+};
+QPC_HD int kin_fd_extra_doubles(int nv) { return nv * nv + 2 * nv; }  // M, rhs / tau_bias
+// s: full KinSmem (kin_load + kin_forward + kin_composite done); M [nv*nv], rhs [nv], tb [nv] scratch; tau [nv] applied
+// torques (global or shared); vd_out [nv]; fc_out optional [ncontacts][3] world contact forces.
+QPC_DEV void kin_forward_dynamics(const DevProgram* __restrict__ pg, KinSmem& s, const ContactModel& cm,
+                                  const double* tau, double* M, double* rhs, double* tb, double* vd_out, double* fc_out) {
+  const int nv = pg->nv, nb = pg->nb;
+  double* ext = s.scr;
+  double* acc = s.scr + 6 * nb;
+  for (int i = QPC_TID; i < 6 * nb; i += QPC_NT) ext[i] = 0.0;
+  for (int i = QPC_TID; i < nv; i += QPC_NT) rhs[i] = 0.0;  // vd = 0 for the bias pass
+  QPC_SYNC();
+  // soft ground contact at the controller's contact points (world frame); one thread per point, then per-body sums
+  for (int c = QPC_TID; c < pg->ncontacts; c += QPC_NT) {
+    const DevContact& dc = pg->contacts[c];
+    const Xf H = body_to_root(s, dc.body);
+    const V3 p = rot(H.R, ld3(dc.pos)) + H.p;
+    const S6 T = body_twist(s, dc.body);
+    const V3 vp = T.v + cross(T.w, p);
+    const double phi = p.z - cm.ground_z;
+    V3 f = mk3(0, 0, 0);
+    if (phi < 0.0) {
+      const double fn = fmax(0.0, -cm.k * phi - cm.d * vp.z);
+      const V3 vt = mk3(vp.x, vp.y, 0.0);
+      const double nvt = sqrt(dot(vt, vt));
+      const double sc = -cm.mu * fn / fmax(nvt, cm.v_eps);
+      f = mk3(sc * vt.x, sc * vt.y, fn);
     }
-    QPC_SYNC();
-  }
-  for (int b = QPC_TID; b < nb; b += QPC_NT) {
-    S6 w = newton_euler(si_load(s.IW + 10 * b), ld6(acc + 6 * b), ld6(s.TW + 6 * b)) - ld6(ext + 6 * b);
-    st6(ext + 6 * b, w);
+    st6(s.A + 6 * c, mk6(cross(p, f), f));  // A (6 x max(nv, nc)) is free after the momentum matrix is no longer needed
+    if (fc_out) st3(fc_out + 3 * c, f);
   }
   QPC_SYNC();
-  // backward: parents accumulate their children's wrenches, deepest level first
-  for (int lvl = pg->nlevels - 2; lvl >= 0; lvl--) {
-    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
-      const int b = pg->level_body[k];
-      S6 w = ld6(ext + 6 * b);
-      for (int c = pg->child_ptr[b]; c < pg->child_ptr[b + 1]; c++) w = w + ld6(ext + 6 * pg->child_idx[c]);
-      st6(ext + 6 * b, w);
+  for (int k = QPC_TID; k < nb * 6; k += QPC_NT) {
+    const int b = k / 6, r = k % 6;
+    double a = 0;
+    for (int c = 0; c < pg->ncontacts; c++)
+      if (pg->contacts[c].body == b) a += s.A[6 * c + r];
+    ext[k] = a;
+  }
+  QPC_SYNC();
+  kin_rnea(pg, s, rhs, ext, acc, tb, false);  // tb = c(q, v) - J'w: bias torques at zero acceleration
+  // mass matrix, composite-rigid-body algorithm: M[i][j] = S_i . (Ic_{body(i)} S_j) when body(j) is body(i) or one of its
+  // ancestors (and symmetric), 0 for velocities on different branches
+  for (int k = QPC_TID; k < nv * nv; k += QPC_NT) {
+    const int i = k / nv, j = k % nv;
+    const int bi = pg->vbody[i], bj = pg->vbody[j];
+    // deeper body = the one whose composite inertia applies; walk up from it to see whether the other is an ancestor
+    int lo_ = bi, hi_ = bj, ci = i, cj = j;
+    bool related = false;
+    for (int pass = 0; pass < 2 && !related; pass++) {
+      for (int b = lo_; b >= 0; b = pg->parent[b])
+        if (b == hi_) {
+          related = true;
+          break;
+        }
+      if (!related) {
+        const int t_ = lo_;
+        lo_ = hi_;
+        hi_ = t_;
+        const int tc = ci;
+        ci = cj;
+        cj = tc;
+      }
+    }
+    double m = 0.0;
+    if (related) m = dot(ld6(s.SW + 6 * cj), si_mul(si_load(s.IC + 10 * lo_), ld6(s.SW + 6 * ci)));
+    M[k] = m;
+  }
+  for (int i = QPC_TID; i < nv; i += QPC_NT) rhs[i] = tau[i] - tb[i];
+  QPC_SYNC();
+  // Cholesky M = L L' in place (lower triangle), column by column, then the two triangular solves
+  for (int j = 0; j < nv; j++) {
+    if (QPC_TID == 0) M[j * nv + j] = sqrt(M[j * nv + j]);
+    QPC_SYNC();
+    const double d = M[j * nv + j];
+    for (int i = j + 1 + QPC_TID; i < nv; i += QPC_NT) M[i * nv + j] /= d;
+    QPC_SYNC();
+    for (int k = QPC_TID; k < (nv - j - 1) * (nv - j - 1); k += QPC_NT) {
+      const int i = j + 1 + k / (nv - j - 1), c = j + 1 + k % (nv - j - 1);
+      if (c <= i) M[i * nv + c] -= M[i * nv + j] * M[c * nv + j];
     }
     QPC_SYNC();
   }
-  for (int c = QPC_TID; c < nv; c += QPC_NT) {
-    const int b = pg->vbody[c];
-    double tau = dot(ld6(s.SW + 6 * c), ld6(ext + 6 * b));
-    if (b == pg->floating) tau = 0.0;  // zero_floating_joint_torques! (momentum.jl:93-97)
-    tau_out[c] = tau;
+  if (QPC_TID == 0) {  // nv <= 64: the substitutions are a serial 2 nv^2 flops
+    for (int i = 0; i < nv; i++) {
+      double a = rhs[i];
+      for (int c = 0; c < i; c++) a -= M[i * nv + c] * rhs[c];
+      rhs[i] = a / M[i * nv + i];
+    }
+    for (int i = nv - 1; i >= 0; i--) {
+      double a = rhs[i];
+      for (int c = i + 1; c < nv; c++) a -= M[c * nv + i] * rhs[c];
+      rhs[i] = a / M[i * nv + i];
+    }
   }
+  QPC_SYNC();
+  for (int i = QPC_TID; i < nv; i += QPC_NT) vd_out[i] = rhs[i];
   QPC_SYNC();
 }
 

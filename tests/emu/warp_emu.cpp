@@ -163,7 +163,7 @@ extern "C" {
 int emu_warp_solve_qp_batch(int64_t B, int32_t n, int32_t mg, int32_t nbx, const double* P, const double* qv, const double* G,
                             const double* lg, const double* lb, const double* ub, double rho, double alpha,
                             double eps_abs, double eps_rel, double eps_prim_inf, int32_t max_iter, int32_t adaptive_rho,
-                            double adaptive_rho_tolerance, double kappa, double growth, int32_t first, int32_t check,
+                            double adaptive_rho_tolerance, double kappa, double growth, int32_t first, int32_t check, int32_t aitken,
                             int32_t paa_diag, int32_t warm, double* x, double* y, double* rho_io, int32_t* status,
                             int32_t* iters, double* res, int32_t* nfac, int32_t* fallback, double* dbg) {
   if (!(mg == 24 && n - nbx == 21 && nbx >= 1 && nbx <= 32)) return -1;
@@ -187,6 +187,7 @@ int emu_warp_solve_qp_batch(int64_t B, int32_t n, int32_t mg, int32_t nbx, const
   wp.growth = growth;
   wp.first = first;
   wp.check = check;
+  wp.aitken = aitken;
   std::vector<double> smem(WarpSolver<24, 21>::SMEM_DOUBLES + 8);
   for (int64_t i = 0; i < B; i++) {
     Job job;

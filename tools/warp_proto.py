@@ -40,7 +40,7 @@ def reduce_qp(P, q, G, b, nb):
 
 
 def solve(P, q, G, lg, lb, ub, eps_abs=1e-5, eps_rel=1e-5, max_iter=5000, rho0=0.1, alpha=1.6, check=5, tol=5.0,
-          kappa=30.0, first=25, growth=2.0, eq_boost=1e3, eps_pinf=1e-4, jump=False):
+          kappa=30.0, first=25, growth=1.35, eq_boost=1e3, eps_pinf=1e-4, aitken=25, cap=10**9, minstep=25):
     nb = lb.shape[0]; n = P.shape[0]; na = n - nb
     r = reduce_qp(P, q, G, lg, nb); H, h, A3, b3, W, xa0 = r["H"], r["h"], r["A3"], r["b3"], r["W"], r["xa0"]
     eq = (ub - lb) < 1e-4
@@ -54,7 +54,7 @@ def solve(P, q, G, lg, lb, ub, eps_abs=1e-5, eps_rel=1e-5, max_iter=5000, rho0=0
     rv, T, t0 = factor(rho, actv); nfac = 1; nadapt = 0
     z = np.zeros(nb); y = np.zeros(nb); bn = np.abs(lg).max()
     nxt = first
-    it = 0; xprev = None; njump = 0; rp_last = None
+    it = 0; sprev = None; dprev = None; njump = 0; rp_last = None
     while it < max_iter:
         it += 1
         v = rv * z - y; xt = T @ v + t0
@@ -70,20 +70,38 @@ def solve(P, q, G, lg, lb, ub, eps_abs=1e-5, eps_rel=1e-5, max_iter=5000, rho0=0
         pok = rp < eps_abs + eps_rel * ps
         if pok and rd < eps_abs + eps_rel * ds:
             return x, 1, it, nfac, nadapt, njump
-        # dual drift: z frozen and x~ stationary => y moves by a constant d = dy per iteration (T d = 0) until a clipped row
-        # releases; jump over those iterations (an extrapolation of the dual -- ADMM converges from any (z, y))
-        if jump and not adapt and it < max_iter and np.array_equal(z, zold) and xprev is not None and \
-                np.abs(xt - xprev).max() <= 1e-12 * max(1.0, np.abs(xt).max()):
-            dyr = dy / rv; yr = y / rv
-            lowa = (z <= lb) & (dyr > 0); upa = (z >= ub) & (dyr < 0)
-            m = lowa | upa
-            N = np.inf
-            if m.any():
-                N = np.floor(np.min(-yr[m] / dyr[m])) - 1
-            N = int(min(N, max_iter - 1 - it, (nxt - 1 - it) if nxt > it else 0))
-            if N > 0:
-                y = y + N * dy; it += N; njump += N
-        xprev = xt.copy()
+        # Extrapolation of slowly converging solves (every `aitken` iterations, between adaptations): once the active set
+        # has settled the iteration is affine, s+ = M s + c on s = (z, y); when one real mode dominates, successive
+        # increments are parallel, d_k = r d_{k-1}, and the limit is s + d r / (1 - r) (Aitken).  r -> 1 is the dual drift
+        # of a wrongly active row.  The step is cut so that no clipped row reaches its release point and no interior row
+        # leaves the box: the active set, hence the affine regime, is preserved; ADMM then continues from the new point.
+        if aitken and not adapt and it % aitken == 0 and it < max_iter:
+            sv = np.concatenate([z, y])
+            if sprev is not None:
+                d = sv - sprev
+                if dprev is not None:
+                    dd = d @ d; pp = dprev @ dprev; dp = d @ dprev
+                    if dd > 0 and pp > 0:
+                        cosv = dp / np.sqrt(dd * pp); rr = dp / pp
+                        if cosv > 1 - 1e-4 and 0 < rr < 1 - 1e-12:
+                            gain = rr / (1 - rr)
+                            dz = d[:nb]; dyv = d[nb:]
+                            clipped = ((z <= lb) | (z >= ub)) & ~eq
+                            m1 = clipped & (y * dyv < 0)
+                            if m1.any(): gain = min(gain, 0.9 * np.min(-y[m1] / dyv[m1]))
+                            inter = ~clipped & ~eq
+                            m2 = inter & (dz > 0)
+                            if m2.any(): gain = min(gain, 0.9 * np.min((ub[m2] - z[m2]) / dz[m2]))
+                            m3 = inter & (dz < 0)
+                            if m3.any(): gain = min(gain, 0.9 * np.min((lb[m3] - z[m3]) / dz[m3]))
+                            if gain >= 1.0:
+                                sn = sv + gain * d
+                                z = np.clip(sn[:nb], lb, ub); y = sn[nb:]
+                                njump += 1
+                                sprev = None; dprev = None
+                                continue
+                dprev = d
+            sprev = sv
         # primal infeasibility certificate of {A3 x = b3, lb <= x <= ub}: dy + A3'mu = 0, u'dy+ + l'dy- + b3'mu < 0
         ndy = np.abs(dy).max()
         if not pok and ndy > eps_pinf:
@@ -92,7 +110,7 @@ def solve(P, q, G, lg, lb, ub, eps_abs=1e-5, eps_rel=1e-5, max_iter=5000, rho0=0
             if sup < -eps_pinf * ndy and np.abs(dy + A3.T @ mu).max() < eps_pinf * ndy:
                 return x, -3, it, nfac, nadapt, njump
         if adapt:
-            nadapt += 1; nxt = int(np.ceil(nxt * growth))
+            nadapt += 1; nxt = max(min(int(np.ceil(nxt * growth)), nxt + cap), nxt + minstep)
             # rho floor: the explicit inverse T = (H + diag(rho))^-1 carries a rounding floor ~ eps_mach |x| lambda_max / rho_row
             # on the primal residual; keep it below eps_abs (lambda_max <= trace(H) = nb cs)
             rho_floor = kappa * 2.2e-16 * max(np.abs(xt).max(), np.abs(z).max(), 1.0) * nb * cs / eps_abs
@@ -105,6 +123,7 @@ def solve(P, q, G, lg, lb, ub, eps_abs=1e-5, eps_rel=1e-5, max_iter=5000, rho0=0
                 if big: rho = rn
                 actv = na_
                 rv, T, t0 = factor(rho, actv); nfac += 1
+                sprev = None; dprev = None
     return x, -2, max_iter, nfac, nadapt, njump
 
 
@@ -137,7 +156,7 @@ if __name__ == "__main__":
     print("reference statuses:", dict(zip(*np.unique(sr, return_counts=True))))
     base = [admm(*stack(a, i), **kw) for i in range(B)]
     print(f"{'osqp form':30s} iters mean {np.mean([r[3] for r in base]):7.1f} max {np.max([r[3] for r in base]):6d} nfac {np.mean([r[4] for r in base]):.2f}")
-    variants = [(f"k{k:g} f{f} g{g:g}", dict(kappa=k, first=f, growth=g, jump=False)) for k in (10.0, 30.0, 50.0) for f, g in ((25, 2.0), (20, 2.0), (10, 3.0))]
+    variants = [(f"k{k:g} f{f} g{g:g}", dict(kappa=k, first=f, growth=g)) for k in (10.0, 30.0, 50.0) for f, g in ((25, 2.0), (20, 2.0), (10, 3.0))]
     for name, kk in variants:
         rs = [solve(a["P"][i], a["q"][i], a["G"][i], a["lg"][i], a["lb"][i], a["ub"][i], **{**kw, **kk}) for i in range(B)]
         its = np.array([r[2] for r in rs]); nf = np.array([r[3] for r in rs]); nad = np.array([r[4] for r in rs]); stt = np.array([r[1] for r in rs])
