@@ -219,6 +219,24 @@ int qpc_reset_warm_start(qpc_controller*); /* forget the stored iterates: the ne
 int qpc_step_batch(qpc_controller*, int64_t B, double* q, double* v, const qpc_batch_in* in, const qpc_batch_out* out,
                    double dt, int32_t nsteps, int32_t flags, void* stream);
 
+/* The same loop with a PLANT (notebooks/Standing controller.ipynb:202-214: simulate(state, T, PeriodicController(tau, dt,
+ * controller)) -- the simulator applies the commanded torques, the environment answers with contact forces): after every
+ * control tick of period dt the state is advanced by `substeps` steps of dt / substeps of the forward dynamics
+ * vd = M(q)^-1 (tau - c(q, v) + sum J'f) (composite-rigid-body mass matrix, Cholesky, RNEA bias) with tau held
+ * (PeriodicController's zero-order hold) and every ContactPoint of the controller pressed against the half-space
+ * z >= ground_z by a spring-damper normal force max(0, -k phi - d phidot) with regularised Coulomb friction
+ * -mu f_n v_t / max(|v_t|, v_eps).  Semi-implicit Euler on the configuration manifold, as qpc_step_batch. */
+typedef struct {
+  double stiffness; /* k [N/m] per contact point */
+  double damping;   /* d [N s/m] per contact point */
+  double mu;        /* friction coefficient of the ground */
+  double v_eps;     /* [m/s] sliding speed below which friction is proportional to it */
+  double ground_z;  /* height of the ground plane in the world frame */
+} qpc_contact_model;
+int qpc_simulate_batch(qpc_controller*, int64_t B, double* q, double* v, const qpc_batch_in* in, const qpc_batch_out* out,
+                       const qpc_contact_model* plant, double dt, int32_t substeps, int32_t nticks, int32_t flags,
+                       void* stream);
+
 /* ---- stage-level entry points (parity tests; the tick above is their composition) -------------------------------- */
 /* kinematics + QP assembly only: writes the condensed QP of every instance (device or host pointers per flags):
  * P [B][n*n], qv [B][n], G [B][mg*n], lg/ug [B][mg], lb/ub [B][nbox], desired_out [B][ndes] */

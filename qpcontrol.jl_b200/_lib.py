@@ -51,6 +51,11 @@ class qpc_batch_in(C.Structure):
                 ("task_weight_matrix", C.c_void_p), ("task_weight_matrix_stride", C.c_int64)]
 
 
+class qpc_contact_model(C.Structure):
+    _fields_ = [("stiffness", C.c_double), ("damping", C.c_double), ("mu", C.c_double), ("v_eps", C.c_double),
+                ("ground_z", C.c_double)]
+
+
 class qpc_batch_out(C.Structure):
     _fields_ = [("tau", C.c_void_p), ("vdot", C.c_void_p), ("wrench", C.c_void_p), ("status", C.c_void_p),
                 ("iters", C.c_void_p), ("residuals", C.c_void_p), ("factorizations", C.c_void_p)]
@@ -65,7 +70,7 @@ COMPUTE_SYMBOLS = ["qpc_solve_batch", "qpc_reserve", "qpc_launch_count", "qpc_as
                    "qpc_set_profiling", "qpc_stage_times", "qpc_measure_fp64_peak", "qpc_set_warm_start",
                    "qpc_reset_warm_start", "qpc_step_batch", "qpc_set_admm_elimination", "qpc_admm_eliminated",
                    "qpc_set_admm_warp", "qpc_admm_warp", "qpc_solve_batch_multi", "qpc_pin_host_buffer",
-                   "qpc_unpin_host_buffer"]
+                   "qpc_unpin_host_buffer", "qpc_simulate_batch"]
 
 _libs = {}
 
@@ -371,6 +376,24 @@ class DeviceController:
     def admm_warp(self) -> bool:
         """True when the next tick runs the one-warp-per-QP ADMM kernel."""
         return bool(self.lib.qpc_admm_warp(self.h.ctrl))
+
+    def simulate_host(self, q, v, dt: float, nticks: int, ground_z: float, substeps: int = 4, stiffness: float = 5e4,
+                      damping: float = 1e3, mu: float = 0.8, v_eps: float = 1e-2, contact_weight=None,
+                      contact_maxnormalforce=None):
+        """`nticks` control ticks of period dt with a PLANT between them (qpc_simulate_batch): forward dynamics under a
+        soft ground contact at z = ground_z, `substeps` integration steps per tick.  Returns (q, v, last tick's result)."""
+        h = self.h
+        h.sync_defaults()
+        q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, None, contact_weight, contact_maxnormalforce)
+        q, v = q.copy(), v.copy()
+        res = _alloc_out(h, B)
+        bi, bo = h.batch_in(q, v, None, cw, cm), _batch_out(res)
+        plant = qpc_contact_model(stiffness, damping, mu, v_eps, ground_z)
+        check(self.lib, self.lib.qpc_simulate_batch(h.ctrl, C.c_int64(B), C.c_void_p(q.ctypes.data),
+                                                    C.c_void_p(v.ctypes.data), C.byref(bi), C.byref(bo), C.byref(plant),
+                                                    C.c_double(dt), C.c_int32(substeps), C.c_int32(nticks),
+                                                    C.c_int32(HOST_PTRS), None), "qpc_simulate_batch")
+        return q, v, res
 
     def step_host(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None,
                   task_weight=None, contact_geometry=None):

@@ -126,6 +126,15 @@ class MomentumBasedController:
     def reset_warm_start(self):
         self.finalize().reset_warm_start()
 
+    def simulate_plant(self, q, v, dt: float, nticks: int, ground_z: float, substeps: int = 8, check: bool = True, **plant):
+        """`simulate(state, T, PeriodicController(tau, dt, controller))` of notebooks/Standing controller.ipynb:202-214 for a
+        batch, WITH a plant: after every control tick the forward dynamics under a soft ground contact at z = ground_z
+        advances the robots by `substeps` steps of dt / substeps (qpc_simulate_batch).  Returns (q, v, last result)."""
+        q, v, res = self.finalize().simulate_host(q, v, dt, nticks, ground_z, substeps=substeps, **plant)
+        if check:
+            checkstatus(res.status)
+        return q, v, res
+
     def simulate(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None,
                  check: bool = True):
         """Closed loop of `nsteps` control ticks at period `dt` for B instances, on the device

@@ -17,6 +17,7 @@ struct DeviceBuffers {
   double *des = nullptr, *x = nullptr, *y = nullptr;
   double* rho = nullptr;  // [capB] rho every slot ended its last accepted solve with (<= 0: none) -- warm start
   double* ksave = nullptr;  // [capB][kin_save_doubles] kinematic state handed from assembly to inverse dynamics
+  double* anchor = nullptr; // [capB][ncontacts][3] tangential-spring anchors of the plant's contact model (qpc_simulate_batch)
   // staging for QPC_HOST_PTRS
   double *q = nullptr, *v = nullptr, *desired = nullptr, *cw = nullptr, *cm = nullptr, *tw = nullptr, *cg = nullptr;
   double *tau = nullptr, *vdot = nullptr, *wrench = nullptr, *res = nullptr;
@@ -248,6 +249,29 @@ qpc_inverse_dynamics_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuf
   }
 }
 
+// ---- the plant of the closed loop: forward dynamics under a soft ground contact (kin.cuh: kin_forward_dynamics) ------------
+__global__ void __launch_bounds__(ASM_THREADS)
+qpc_forward_dynamics_kernel(const DevProgram* __restrict__ pg, const double* __restrict__ q, const double* __restrict__ v,
+                            const double* __restrict__ tau, ContactModel cm, double* vd_out, double* anchor, long long B) {
+  extern __shared__ double smem[];
+  const int ks = kin_smem_doubles(pg->nb, pg->nq, pg->nv, pg->ndes, pg->ncontacts, pg->N);
+  for (long long inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    KinSmem s = kin_layout(smem, pg->nb, pg->nq, pg->nv, pg->ndes, pg->ncontacts, pg->N);
+    double* M = smem + ks;
+    BatchIO io;
+    io.q = q;
+    io.v = v;
+    io.desired = nullptr;
+    io.cweight = io.cmaxnf = nullptr;
+    io.desired_stride = io.contact_stride = 0;
+    kin_load(pg, io, inst, s);
+    kin_forward(pg, s);
+    kin_composite(pg, s);
+    kin_forward_dynamics(pg, s, cm, tau + inst * pg->nv, M, M + pg->nv * pg->nv, M + pg->nv * pg->nv + pg->nv,
+                         vd_out + inst * pg->nv, nullptr, anchor ? anchor + inst * 3 * pg->ncontacts : nullptr);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 template <class T>
 static cudaError_t grow(T*& p, long long count) {
@@ -274,6 +298,8 @@ static int ensure_capacity(qpc_controller* c, long long B, long long dstride, lo
     CUDA_TRY(grow(b.y, B * (mg + nbx)));
     CUDA_TRY(grow(b.rho, B));
     CUDA_TRY(grow(b.ksave, B * kin_save_doubles(p.nb, p.nv, p.ncontacts, p.N)));
+    CUDA_TRY(grow(b.anchor, B * 3 * (p.ncontacts > 0 ? p.ncontacts : 1)));
+    CUDA_TRY(cudaMemset(b.anchor, 0, sizeof(double) * (size_t)B * 3 * (p.ncontacts > 0 ? p.ncontacts : 1)));
     CUDA_TRY(cudaMemset(b.rho, 0, sizeof(double) * (size_t)B));
     CUDA_TRY(grow(b.q, B * p.nq));
     CUDA_TRY(grow(b.v, B * p.nv));
@@ -343,6 +369,7 @@ static cudaError_t raise_dyn_smem(K kernel, int bytes, int (&mark)[64]) {
   if (e == cudaSuccess) mark[dev] = bytes;
   return e;
 }
+static int g_mark_fd[64];
 static int g_mark_asm[64], g_mark_id[64], g_mark_admm128[64], g_mark_admm512[64], g_mark_kinwarp[64], g_mark_idsaved[64];
 // ---- ADMM dispatch: register-resident kernel when the KKT matrix fits the register file, shared-memory kernel otherwise
 // returns a code TC * 100 + NB, or 0 for the shared-memory kernel
@@ -788,7 +815,7 @@ void qpc_controller_destroy(qpc_controller* c) {
     cudaSetDevice(c->be.device);
     DeviceBuffers& b = c->be.buf;
     void* ptrs[] = {b.P, b.qv, b.G, b.lg, b.ug, b.lb, b.ub, b.des, b.x, b.y, b.q, b.v, b.desired, b.cw,
-                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.ksave, b.tw, b.cg, b.twm, c->be.d_fb_list, c->be.d_fb_count};
+                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.ksave, b.anchor, b.tw, b.cg, b.twm, c->be.d_fb_list, c->be.d_fb_count};
     for (int i = 0; i < 4; i++)
       if (c->be.ev[i]) cudaEventDestroy(c->be.ev[i]);
     for (void* p : ptrs)
@@ -1053,6 +1080,9 @@ int qpc_reset_warm_start(qpc_controller* c) {
   std::lock_guard<std::mutex> lock(c->be.mu);
   CUDA_TRY(cudaSetDevice(c->be.device));
   if (c->be.buf.rho && c->be.buf.capB > 0) {
+    if (c->be.buf.anchor)
+      CUDA_TRY(cudaMemsetAsync(c->be.buf.anchor, 0, sizeof(double) * (size_t)c->be.buf.capB * 3 *
+                               (c->prog.ncontacts > 0 ? c->prog.ncontacts : 1), c->be.stream));
     CUDA_TRY(cudaMemsetAsync(c->be.buf.rho, 0, sizeof(double) * (size_t)c->be.buf.capB, c->be.stream));
     CUDA_TRY(cudaStreamSynchronize(c->be.stream));
   }
@@ -1101,8 +1131,26 @@ __global__ void qpc_integrate_kernel(const DevProgram* __restrict__ pg, double* 
   }
 }
 
+static int step_impl(qpc_controller* c, int64_t B, double* q, double* v, const qpc_batch_in* in, const qpc_batch_out* out,
+                     double dt, int32_t nsteps, int32_t flags, void* stream_, const qpc_contact_model* plant, int32_t substeps);
+
 int qpc_step_batch(qpc_controller* c, int64_t B, double* q, double* v, const qpc_batch_in* in, const qpc_batch_out* out,
                    double dt, int32_t nsteps, int32_t flags, void* stream_) {
+  return step_impl(c, B, q, v, in, out, dt, nsteps, flags, stream_, nullptr, 1);
+}
+
+// Closed loop with a PLANT: every control tick (period dt, zero-order hold on tau: RigidBodySim's PeriodicController) is
+// followed by `substeps` integration steps of dt / substeps of the forward dynamics under the soft ground contact.
+int qpc_simulate_batch(qpc_controller* c, int64_t B, double* q, double* v, const qpc_batch_in* in, const qpc_batch_out* out,
+                       const qpc_contact_model* plant, double dt, int32_t substeps, int32_t nticks, int32_t flags,
+                       void* stream_) {
+  if (!plant || substeps < 1 || !(plant->stiffness >= 0.0) || !(plant->damping >= 0.0) || !(plant->v_eps > 0.0))
+    return qpc_fail(QPC_ERR_ARG, "qpc_simulate_batch: bad contact model / substeps");
+  return step_impl(c, B, q, v, in, out, dt, nticks, flags, stream_, plant, substeps);
+}
+
+static int step_impl(qpc_controller* c, int64_t B, double* q, double* v, const qpc_batch_in* in, const qpc_batch_out* out,
+                     double dt, int32_t nsteps, int32_t flags, void* stream_, const qpc_contact_model* plant, int32_t substeps) {
   if (!c || !c->finalized) return qpc_fail(QPC_ERR_STATE, "controller not finalized");
   if (!q || !v || B < 0 || nsteps < 0 || !(dt > 0.0)) return qpc_fail(QPC_ERR_ARG, "qpc_step_batch: bad arguments");
   if (B == 0 || nsteps == 0) return QPC_OK;
@@ -1174,11 +1222,32 @@ int qpc_step_batch(qpc_controller* c, int64_t B, double* q, double* v, const qpc
   double* vdot = o.vdot ? o.vdot : b.vdot;
   int* status = o.status ? o.status : b.status;
   const DevProgram* dp = (const DevProgram*)c->be.d_prog;
+  double* tau_dev = o.tau ? o.tau : b.tau;  // the plant needs the torques even when the caller does not ask for them
+  int fdsm = 0;
+  ContactModel cmodel{0, 0, 0, 1, 0};
+  if (plant) {
+    fdsm = (kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) + kin_fd_extra_doubles(p.nv)) * 8;
+    if (fdsm > 227 * 1024) return qpc_fail(QPC_ERR_LIMIT, "mechanism too large for the forward-dynamics kernel");
+    CUDA_TRY(raise_dyn_smem(qpc_forward_dynamics_kernel, fdsm, g_mark_fd));
+    cmodel = ContactModel{plant->stiffness, plant->damping, plant->mu, plant->v_eps, plant->ground_z};
+  }
+  double* anchor = plant ? b.anchor : nullptr;  // persists across calls; qpc_reset_warm_start clears it
   for (int k = 0; k < nsteps; k++) {
-    rc = run_tick(c, B, io, o.tau, vdot, o.wrench, status, o.iters, o.residuals, o.factorizations, s);
+    rc = run_tick(c, B, io, plant ? tau_dev : o.tau, vdot, o.wrench, status, o.iters, o.residuals, o.factorizations, s);
     if (rc) return rc;
-    qpc_integrate_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(dp, dq, dv, vdot, status, dt, B);
-    c->be.launches += 1;
+    if (!plant) {
+      qpc_integrate_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(dp, dq, dv, vdot, status, dt, B);
+      c->be.launches += 1;
+    } else {
+      // the commanded accelerations stay in `vdot` (what the caller reads); the plant's go through the x workspace's
+      // neighbour b.vdot when the caller supplied its own buffer, else a scratch view of b.tau's twin
+      double* vd_sim = b.ksave;  // [B][>= nv] scratch: the saved kinematic state is dead once the tick has finished
+      for (int ss = 0; ss < substeps; ss++) {
+        qpc_forward_dynamics_kernel<<<launch_grid(B), ASM_THREADS, fdsm, s>>>(dp, dq, dv, tau_dev, cmodel, vd_sim, anchor, B);
+        qpc_integrate_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(dp, dq, dv, vd_sim, status, dt / substeps, B);
+        c->be.launches += 2;
+      }
+    }
   }
   CUDA_TRY(cudaGetLastError());
   if (host) {

@@ -578,8 +578,13 @@ struct ContactModel {
 QPC_HD int kin_fd_extra_doubles(int nv) { return nv * nv + 2 * nv; }  // M, rhs / tau_bias
 // s: full KinSmem (kin_load + kin_forward + kin_composite done); M [nv*nv], rhs [nv], tb [nv] scratch; tau [nv] applied
 // torques (global or shared); vd_out [nv]; fc_out optional [ncontacts][3] world contact forces.
+// anchor: optional per-contact state [ncontacts][3] = (x, y, in-contact flag) of the tangential spring (stick): with it the
+// tangential force is -k (p_t - anchor) - d v_t clipped to the cone mu f_n (the anchor slides along when clipped), the
+// viscoelastic Coulomb model; without it the force is the regularised Coulomb law, whose stick regime is a damper of
+// coefficient mu f_n / v_eps that an explicit integrator only tolerates for light loads.
 QPC_DEV void kin_forward_dynamics(const DevProgram* __restrict__ pg, KinSmem& s, const ContactModel& cm,
-                                  const double* tau, double* M, double* rhs, double* tb, double* vd_out, double* fc_out) {
+                                  const double* tau, double* M, double* rhs, double* tb, double* vd_out, double* fc_out,
+                                  double* anchor = nullptr) {
   const int nv = pg->nv, nb = pg->nb;
   double* ext = s.scr;
   double* acc = s.scr + 6 * nb;
@@ -597,10 +602,33 @@ QPC_DEV void kin_forward_dynamics(const DevProgram* __restrict__ pg, KinSmem& s,
     V3 f = mk3(0, 0, 0);
     if (phi < 0.0) {
       const double fn = fmax(0.0, -cm.k * phi - cm.d * vp.z);
-      const V3 vt = mk3(vp.x, vp.y, 0.0);
-      const double nvt = sqrt(dot(vt, vt));
-      const double sc = -cm.mu * fn / fmax(nvt, cm.v_eps);
-      f = mk3(sc * vt.x, sc * vt.y, fn);
+      if (anchor) {
+        double* a = anchor + 3 * c;
+        if (a[2] == 0.0) {  // touch-down: the tangential spring starts unloaded
+          a[0] = p.x;
+          a[1] = p.y;
+          a[2] = 1.0;
+        }
+        double fx = -cm.k * (p.x - a[0]) - cm.d * vp.x, fy = -cm.k * (p.y - a[1]) - cm.d * vp.y;
+        const double ft = sqrt(fx * fx + fy * fy), lim = cm.mu * fn;
+        if (ft > lim) {  // sliding: force on the cone, anchor dragged so that the spring carries exactly that force
+          const double sc = ft > 0.0 ? lim / ft : 0.0;
+          fx *= sc;
+          fy *= sc;
+          if (cm.k > 0.0) {
+            a[0] = p.x + (fx + cm.d * vp.x) / cm.k;
+            a[1] = p.y + (fy + cm.d * vp.y) / cm.k;
+          }
+        }
+        f = mk3(fx, fy, fn);
+      } else {
+        const V3 vt = mk3(vp.x, vp.y, 0.0);
+        const double nvt = sqrt(dot(vt, vt));
+        const double sc = -cm.mu * fn / fmax(nvt, cm.v_eps);
+        f = mk3(sc * vt.x, sc * vt.y, fn);
+      }
+    } else if (anchor) {
+      anchor[3 * c + 2] = 0.0;  // lift-off
     }
     st6(s.A + 6 * c, mk6(cross(p, f), f));  // A (6 x max(nv, nc)) is free after the momentum matrix is no longer needed
     if (fc_out) st3(fc_out + 3 * c, f);

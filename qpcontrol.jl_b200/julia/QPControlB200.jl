@@ -299,6 +299,33 @@ function simulate!(c::MomentumBasedController, q::Matrix{Float64}, v::Matrix{Flo
     tau, vdot, wrench, status
 end
 
+# The same loop with a PLANT between the control ticks (qpc_simulate_batch): forward dynamics vd = M^-1 (tau - c + J'f) under
+# a soft ground contact at z = groundz, `substeps` integration steps per control period, tau held in between
+# (PeriodicController).  stiffness / damping per contact point, mu of the ground.
+struct qpc_contact_model
+    stiffness::Cdouble; damping::Cdouble; mu::Cdouble; v_eps::Cdouble; ground_z::Cdouble
+end
+function simulateplant!(c::MomentumBasedController, q::Matrix{Float64}, v::Matrix{Float64}, dt::Float64, nticks::Integer;
+                        groundz::Float64=0.0, substeps::Integer=8, stiffness=5e4, damping=1e3, mu=0.8, v_eps=1e-2,
+                        check::Bool=true)
+    c.initialized || initialize!(c)
+    syncdefaults!(c)
+    B = size(q, 2)
+    nc = length(c.contacts)
+    tau = zeros(size(v)); vdot = similar(v); wrench = zeros(6, nc, B); status = zeros(Int32, B)
+    GC.@preserve q v tau vdot wrench status begin
+        bin = qpc_batch_in(C_NULL, C_NULL, C_NULL, 0, C_NULL, C_NULL, 0)
+        bout = qpc_batch_out(pointer(tau), pointer(vdot), pointer(wrench), pointer(status), C_NULL, C_NULL, C_NULL)
+        plant = qpc_contact_model(stiffness, damping, mu, v_eps, groundz)
+        QPControlB200.check(ccall((:qpc_simulate_batch, LIB[]), Cint,
+                                  (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ref{qpc_batch_in}, Ref{qpc_batch_out},
+                                   Ref{qpc_contact_model}, Cdouble, Int32, Int32, Int32, Ptr{Cvoid}),
+                                  c.handle, B, q, v, bin, bout, plant, dt, substeps, nticks, 0, C_NULL), "qpc_simulate_batch")
+    end
+    check && checkstatus(status)
+    tau, vdot, wrench, status
+end
+
 # ---- StandingController (reference src/highlevel/standing.jl:18-56); the PD laws of :58-85 run on the device ---------
 struct StandingController{N}
     lowlevel::MomentumBasedController{N}

@@ -194,4 +194,33 @@ int emu_id_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const dou
   return QPC_OK;
 }
 
+// forward dynamics under the soft ground contact (kin.cuh: kin_forward_dynamics) for given applied torques
+int emu_forward_dynamics_batch(qpc_controller* c, int64_t B, const double* q, const double* v, const double* tau,
+                               double k, double d, double mu, double v_eps, double ground_z, double* vd_out,
+                               double* fc_out) {
+  const DevProgram& p = c->prog;
+  BatchIO io;
+  io.q = q;
+  io.v = v;
+  io.desired = nullptr;
+  io.cweight = io.cmaxnf = nullptr;
+  io.desired_stride = io.contact_stride = 0;
+  ContactModel cm{k, d, mu, v_eps, ground_z};
+#pragma omp parallel
+  {
+    std::vector<double> ksm(kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) + kin_fd_extra_doubles(p.nv));
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t i = 0; i < B; i++) {
+      KinSmem s = kin_layout(ksm.data(), p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N);
+      double* M = ksm.data() + kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N);
+      kin_load(&p, io, i, s);
+      kin_forward(&p, s);
+      kin_composite(&p, s);
+      kin_forward_dynamics(&p, s, cm, tau + i * p.nv, M, M + p.nv * p.nv, M + p.nv * p.nv + p.nv, vd_out + i * p.nv,
+                           fc_out ? fc_out + i * p.ncontacts * 3 : nullptr);
+    }
+  }
+  return QPC_OK;
+}
+
 }  // extern "C"

@@ -63,6 +63,18 @@ class EmuController:
         res.fallback = w["fallback"]
         return res
 
+    def forward_dynamics(self, q, v, tau, k=5e4, d=1e3, mu=0.8, v_eps=1e-2, ground_z=-1e9):
+        """vd = M^-1 (tau - c + J'w) with the soft ground contact of kin.cuh (ground far below by default: no contact)."""
+        h = self.h
+        q, v, tau = (np.atleast_2d(L._c(a)) for a in (q, v, tau))
+        B = q.shape[0]
+        vd = np.zeros((B, h.nv)); fc = np.zeros((B, max(h.ncontacts, 1), 3))
+        L.check(self.lib, self.lib.emu_forward_dynamics_batch(h.ctrl, C.c_int64(B), L._p(q), L._p(v), L._p(tau),
+                                                               C.c_double(k), C.c_double(d), C.c_double(mu),
+                                                               C.c_double(v_eps), C.c_double(ground_z), L._p(vd), L._p(fc)),
+                "emu_forward_dynamics_batch")
+        return vd, fc[:, :h.ncontacts]
+
     def assemble(self, q, v, desired=None, cw=None, cm=None):
         h = self.h
         h.sync_defaults()
