@@ -244,9 +244,17 @@ def _require(a, shape, name, dtype=np.float64):
 
 
 def _require_dev(t, shape, name, at_least=False):
-    """Device tensor handed to the C ABI: contiguous, and of (at least, for outputs larger than the batch) this shape."""
+    """Device tensor handed to the C ABI: contiguous, with the exact shape -- or, with `at_least`, the same row layout and
+    at least as many rows (a larger tensor may back a smaller batch).  Nothing is read or written when a row is empty
+    (e.g. the wrench output of a controller without contacts), so any tensor passes then."""
     sh = tuple(t.shape)
-    ok = len(sh) == len(shape) and sh[1:] == tuple(shape[1:]) and (sh[0] >= shape[0] if at_least else sh[0] == shape[0])
+    need = 1
+    for d in shape:
+        need *= int(d)
+    if at_least:
+        ok = need == 0 or (len(sh) == len(shape) and sh[1:] == tuple(shape[1:]) and sh[0] >= shape[0])
+    else:
+        ok = sh == tuple(shape)
     if not ok or not t.is_contiguous():
         raise ValueError(f"{name} must be a contiguous device tensor of shape {tuple(shape)}; got {sh}")
 

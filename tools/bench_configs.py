@@ -189,7 +189,12 @@ def main():
     print("config 4", json.dumps(r), flush=True)
 
     # ---- config 5 --------------------------------------------------------------------------------------------------
-    sweep = [(30, 30, 16384), (68, 71, 16384), (100, 100, 4096), (143, 178, 1024), (200, 200, 512)]
+    # n in {30, 50, 68, 100, 143, 200} x batch in {1k, 16k, 128k, 1M}, bounded to <= 24 GB of QP data
+    sweep = []
+    for n, m in ((30, 30), (50, 50), (68, 71), (100, 100), (143, 178), (200, 200)):
+        for B in (1024, 16384, 131072, 1 << 20):
+            if 8.0 * B * (n * n + m * n + 3 * n + 3 * m) <= 24e9 and (n + m <= 144 or B <= (16384 if n <= 100 else 1024)):
+                sweep.append((n, m, B))
     if args.quick:
         sweep = [(30, 30, 2048), (68, 71, 2048)]
     result["config5_dense_qp_sweep"] = []
