@@ -107,6 +107,11 @@ typedef struct {
                                      test/controller.jl:232-285; NULL = the matrices given at setup.  The Hessian block of
                                      the task's slack is W + W' (an unsymmetric W is allowed, as in the reference) */
   int64_t task_weight_matrix_stride; /* >= qpc_controller_weight_matrix_doubles(), or 0 to broadcast one row */
+  const double* time;       /* controller time t of the tick -- the first argument of the functors,
+                               (controller::SE3PDController)(t, state), se3pdcontroller.jl:13: [B] (time_stride 1) or
+                               one value for the whole batch (time_stride 0); NULL = 0.  Read only by controllers
+                               with device-side SE3PDControllers (qpc_add_se3pd) */
+  int64_t time_stride;
 } qpc_batch_in;
 
 /* Outputs of one batched tick: what the reference leaves in tau (momentum.jl:75-80), controller.result.vd (:62-64)
@@ -155,6 +160,35 @@ int qpc_standing_setup(qpc_controller*, int32_t linmom_task, int32_t pelvis_task
                        const int32_t* joint_tasks, const int32_t* joints, const double* kp, const double* kd,
                        const double* qref, double com_kp, double com_kd, double pelvis_kp, double pelvis_kd,
                        const double comref[3]);
+/* ---- SE3PDController + SE3Trajectory on the device ----------------------------------------
+ * One `Interpolated` piece (src/trajectories/interpolated.jl:1-60) of a trajectory; a `Piecewise` (piecewise.jl:1-40)
+ * is a list of pieces, piece i active from break_start and evaluated at x - break_start.  Rotations: y0 = unit
+ * quaternion (w, x, y, z) of the start, dy = unit axis and angle = rotation angle of y0 \ yf (interpolated.jl:75-82);
+ * vectors: y0[0..2], dy = yf - y0.  coeffs = ascending coefficients of the polynomial interpolator alpha(theta)
+ * (fit_polynomial.jl), ncoeffs = 0 for the identity.  A `Constant` (constant.jl) is a piece with dy = 0. */
+typedef struct {
+  double break_start, x0, xf;
+  double y0[4], dy[3], angle;
+  double coeffs[6];
+  int32_t ncoeffs, reserved;
+} qpc_interp_piece;
+#define QPC_MAX_SE3PD 4
+#define QPC_MAX_PIECES 6
+/* SE3PDController(base, body, trajectory, weight, gains) (se3pdcontroller.jl:1-11) whose output
+ * Tdref + pd(gains, H, Href, T, Tref) (:13-18) becomes the desired of SpatialAccelerationTask `task` every tick, evaluated
+ * in the assembly kernel at qpc_batch_in.time (the entries of qpc_batch_in.desired for that task are then ignored).
+ * gains: four 3 x 3 row-major matrices K_angular, D_angular, K_linear, D_linear (SE3PDGains in the body frame).
+ * angular / linear: the two components of the SE3Trajectory (src/trajectories/se3.jl:1-27); *_piecewise = 0 evaluates
+ * piece 0 at t itself, 1 clamps t to [pieces[0].break_start, *_break_end] first.  Trajectories are clamped to their
+ * range (Interpolated's clamp = true); returns the controller's index >= 0.  Before qpc_finalize. */
+int qpc_add_se3pd(qpc_controller*, int32_t task, int32_t base_body, int32_t body, const double gains[36],
+                  int32_t n_angular, const qpc_interp_piece* angular, int32_t angular_piecewise, double angular_break_end,
+                  int32_t n_linear, const qpc_interp_piece* linear, int32_t linear_piecewise, double linear_break_end);
+/* controller.trajectory[] = ... / controller.gains[] = ... (both are Refs in the reference, se3pdcontroller.jl:4-6):
+ * replace them between ticks; NULL leaves that part unchanged */
+int qpc_se3pd_update(qpc_controller*, int32_t se3pd, const double* gains,
+                     int32_t n_angular, const qpc_interp_piece* angular, int32_t angular_piecewise, double angular_break_end,
+                     int32_t n_linear, const qpc_interp_piece* linear, int32_t linear_piecewise, double linear_break_end);
 int qpc_set_settings(qpc_controller*, const qpc_settings*);
 /* initialize! (momentum.jl:150-156): freezes the program, builds the device tables on `device` */
 int qpc_finalize(qpc_controller*, int32_t device);

@@ -48,7 +48,27 @@ class qpc_batch_in(C.Structure):
                 ("contact_weight", C.c_void_p), ("contact_maxnormalforce", C.c_void_p), ("contact_stride", C.c_int64),
                 ("task_weight", C.c_void_p), ("task_weight_stride", C.c_int64),
                 ("contact_geometry", C.c_void_p), ("contact_geometry_stride", C.c_int64),
-                ("task_weight_matrix", C.c_void_p), ("task_weight_matrix_stride", C.c_int64)]
+                ("task_weight_matrix", C.c_void_p), ("task_weight_matrix_stride", C.c_int64),
+                ("time", C.c_void_p), ("time_stride", C.c_int64)]
+
+
+class qpc_interp_piece(C.Structure):
+    _fields_ = [("break_start", C.c_double), ("x0", C.c_double), ("xf", C.c_double), ("y0", C.c_double * 4),
+                ("dy", C.c_double * 3), ("angle", C.c_double), ("coeffs", C.c_double * 6), ("ncoeffs", C.c_int32),
+                ("reserved", C.c_int32)]
+
+    @staticmethod
+    def array(pieces):
+        arr = (qpc_interp_piece * len(pieces))()
+        for a, d in zip(arr, pieces):
+            a.break_start, a.x0, a.xf, a.angle = d["break_start"], d["x0"], d["xf"], d["angle"]
+            y0 = np.zeros(4)
+            y0[:len(d["y0"])] = d["y0"]
+            a.y0[:] = y0.tolist()
+            a.dy[:] = np.asarray(d["dy"], dtype=np.float64).tolist()
+            a.ncoeffs = len(d["coeffs"])
+            a.coeffs[:] = (list(map(float, d["coeffs"])) + [0.0] * 6)[:6]
+        return arr
 
 
 class qpc_contact_model(C.Structure):
@@ -65,7 +85,7 @@ SETUP_SYMBOLS = ["qpc_version", "qpc_last_error", "qpc_device_count", "qpc_defau
                  "qpc_mechanism_destroy", "qpc_mechanism_dims", "qpc_controller_create", "qpc_controller_destroy",
                  "qpc_add_contact", "qpc_set_contact_params", "qpc_add_task", "qpc_set_task_desired", "qpc_regularize",
                  "qpc_standing_setup", "qpc_set_settings", "qpc_finalize", "qpc_controller_dims",
-                 "qpc_controller_weight_matrix_doubles"]
+                 "qpc_controller_weight_matrix_doubles", "qpc_add_se3pd", "qpc_se3pd_update"]
 COMPUTE_SYMBOLS = ["qpc_solve_batch", "qpc_reserve", "qpc_launch_count", "qpc_assemble_batch", "qpc_solve_qp_batch",
                    "qpc_set_profiling", "qpc_stage_times", "qpc_measure_fp64_peak", "qpc_set_warm_start",
                    "qpc_reset_warm_start", "qpc_step_batch", "qpc_set_admm_elimination", "qpc_admm_eliminated",
@@ -151,16 +171,36 @@ class Handles:
                 _p(_c(s.joint_kp)), _p(_c(s.joint_kd)), _p(_c(s.joint_ref)), C.c_double(s.com_kp),
                 C.c_double(s.com_kd), C.c_double(s.pelvis_kp), C.c_double(s.pelvis_kd), _p(_c(s.comref))),
                 "qpc_standing_setup")
+        for i, sp in enumerate(program.se3pd):
+            got = check(lib, lib.qpc_add_se3pd(self.ctrl, C.c_int32(sp.task), C.c_int32(sp.controller.base),
+                                               C.c_int32(sp.controller.body), *self._se3pd_args(sp.controller)),
+                        "qpc_add_se3pd")
+            assert got == i
         check(lib, lib.qpc_finalize(self.ctrl, C.c_int32(device)), "qpc_finalize")
         self.sync_defaults()
         dims = [C.c_int32() for _ in range(7)]
         check(lib, lib.qpc_controller_dims(self.ctrl, *[C.byref(d) for d in dims]), "qpc_controller_dims")
         self.nq, self.nv, self.ndes, self.ncontacts, self.n, self.mg, self.nbox = [d.value for d in dims]
 
+    @staticmethod
+    def _se3pd_args(ctl):
+        """gains and the two trajectory components of an SE3PDController in the layout of qpc_add_se3pd"""
+        from .se3pd import compile_trajectory, gains_matrix
+        traj = ctl.trajectory
+        if not (hasattr(traj, "angular") and hasattr(traj, "linear")):
+            raise TypeError("the device evaluates SE3Trajectory references (angular + linear components)")
+        pa, pwa, enda = compile_trajectory(traj.angular, True)
+        pl, pwl, endl = compile_trajectory(traj.linear, False)
+        return (_p(gains_matrix(ctl.gains)), C.c_int32(len(pa)), qpc_interp_piece.array(pa), C.c_int32(int(pwa)),
+                C.c_double(enda), C.c_int32(len(pl)), qpc_interp_piece.array(pl), C.c_int32(int(pwl)), C.c_double(endl))
+
     def sync_defaults(self):
         """Push the current `setdesired!` values and ContactPoint.weight / .maxnormalforce (mutable between ticks in
-        the reference) and the solver settings."""
+        the reference), the SE3PDControllers' trajectory / gains Refs (se3pdcontroller.jl:4-6) and the solver settings.
+        The library re-uploads its tables only when something changed."""
         lib, pr = self.lib, self.program
+        for i, sp in enumerate(pr.se3pd):
+            check(lib, lib.qpc_se3pd_update(self.ctrl, C.c_int32(i), *self._se3pd_args(sp.controller)), "qpc_se3pd_update")
         for i, c in enumerate(pr.contacts):
             check(lib, lib.qpc_set_contact_params(self.ctrl, C.c_int32(i), C.c_double(c.weight),
                                                   C.c_double(c.maxnormalforce)), "qpc_set_contact_params")
@@ -186,7 +226,7 @@ class Handles:
 
     # ---- argument marshalling shared by every compute entry point ----------------------------------------------
     def batch_in(self, q, v, desired, cw, cm, ptr=lambda a: a.ctypes.data, keep=None, task_weight=None,
-                 contact_geometry=None, task_weight_matrix=None):
+                 contact_geometry=None, task_weight_matrix=None, time=None):
         """Builds a qpc_batch_in from arrays (numpy for host pointers; `ptr` extracts the address).  task_weight
         [B, ntasks] / [ntasks] and contact_geometry [B, ncontacts, 7] / [ncontacts, 7] are the per-tick Parameters of
         the reference (task weights; contact position, normal, mu)."""
@@ -208,6 +248,9 @@ class Handles:
         if task_weight_matrix is not None:
             bi.task_weight_matrix = ptr(task_weight_matrix)
             bi.task_weight_matrix_stride = 0 if task_weight_matrix.ndim == 1 else task_weight_matrix.shape[1]
+        if time is not None:  # [B] controller times, or one value (shape () / (1,)) for the whole batch
+            bi.time = ptr(time)
+            bi.time_stride = 1 if time.ndim == 1 and time.shape[0] > 1 else 0
         return bi
 
 
@@ -259,6 +302,16 @@ def _require_dev(t, shape, name, at_least=False):
         raise ValueError(f"{name} must be a contiguous device tensor of shape {tuple(shape)}; got {sh}")
 
 
+def _prep_time(time, B):
+    """Controller time(s) of the tick: None, one value for the batch, or one per instance -> contiguous float64 array"""
+    if time is None:
+        return None
+    t = np.ascontiguousarray(np.atleast_1d(np.asarray(time, dtype=np.float64)))
+    if t.ndim != 1 or t.shape[0] not in (1, B):
+        raise ValueError(f"time must be a scalar or have one entry per instance ({B}); got shape {t.shape}")
+    return t
+
+
 def _check_rows(B, **arrays):
     """Per-instance arrays must have exactly B rows: the C ABI copies B * stride doubles from them (a shorter array would
     be read out of bounds).  `base_ndim` = the number of dimensions of ONE row (a broadcast row has that many)."""
@@ -303,7 +356,7 @@ def _batch_out(res: BatchResult, ptr=lambda a: a.ctypes.data):
 
 
 def solve_host_multi(devs, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None, task_weight=None,
-                     contact_geometry=None) -> BatchResult:
+                     contact_geometry=None, time=None) -> BatchResult:
     """One batch over several devices from this process (qpc_solve_batch_multi): `devs` are DeviceControllers of replicas
     of one program, finalized on different devices; contiguous shards, one host thread per device inside the library."""
     h = devs[0].h
@@ -312,7 +365,7 @@ def solve_host_multi(devs, q, v, desired=None, contact_weight=None, contact_maxn
     q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
     tw, cg = _prep_tick_parameters(h, task_weight, contact_geometry, B)
     res = _alloc_out(h, B)
-    bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg), _batch_out(res)
+    bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg, time=_prep_time(time, B)), _batch_out(res)
     arr = (C.c_void_p * len(devs))(*[d.h.ctrl for d in devs])
     check(devs[0].lib, devs[0].lib.qpc_solve_batch_multi(arr, C.c_int32(len(devs)), C.c_int64(B), C.byref(bi), C.byref(bo)),
           "qpc_solve_batch_multi")
@@ -387,15 +440,15 @@ class DeviceController:
 
     def simulate_host(self, q, v, dt: float, nticks: int, ground_z: float, substeps: int = 4, stiffness: float = 5e4,
                       damping: float = 1e3, mu: float = 0.8, v_eps: float = 1e-2, contact_weight=None,
-                      contact_maxnormalforce=None):
+                      contact_maxnormalforce=None, desired=None, time=None):
         """`nticks` control ticks of period dt with a PLANT between them (qpc_simulate_batch): forward dynamics under a
         soft ground contact at z = ground_z, `substeps` integration steps per tick.  Returns (q, v, last tick's result)."""
         h = self.h
         h.sync_defaults()
-        q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, None, contact_weight, contact_maxnormalforce)
+        q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
         q, v = q.copy(), v.copy()
         res = _alloc_out(h, B)
-        bi, bo = h.batch_in(q, v, None, cw, cm), _batch_out(res)
+        bi, bo = h.batch_in(q, v, desired, cw, cm, time=_prep_time(time, B)), _batch_out(res)  # time: of the first tick
         plant = qpc_contact_model(stiffness, damping, mu, v_eps, ground_z)
         check(self.lib, self.lib.qpc_simulate_batch(h.ctrl, C.c_int64(B), C.c_void_p(q.ctypes.data),
                                                     C.c_void_p(v.ctypes.data), C.byref(bi), C.byref(bo), C.byref(plant),
@@ -404,7 +457,7 @@ class DeviceController:
         return q, v, res
 
     def step_host(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None,
-                  task_weight=None, contact_geometry=None):
+                  task_weight=None, contact_geometry=None, time=None):
         """`nsteps` closed-loop ticks on the device (qpc_step_batch); returns (q, v, result of the last tick)."""
         h = self.h
         h.sync_defaults()
@@ -412,7 +465,7 @@ class DeviceController:
         tw, cg = _prep_tick_parameters(h, task_weight, contact_geometry)
         q, v = q.copy(), v.copy()
         res = _alloc_out(h, B)
-        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg), _batch_out(res)
+        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg, time=_prep_time(time, B)), _batch_out(res)
         check(self.lib, self.lib.qpc_step_batch(h.ctrl, C.c_int64(B), C.c_void_p(q.ctypes.data),
                                                 C.c_void_p(v.ctypes.data), C.byref(bi), C.byref(bo), C.c_double(dt),
                                                 C.c_int32(nsteps), C.c_int32(HOST_PTRS), None), "qpc_step_batch")
@@ -436,8 +489,9 @@ class DeviceController:
                                                 C.c_int32(DEVICE_PTRS), C.c_void_p(stream)), "qpc_step_batch")
 
     def solve_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None, task_weight=None,
-                   contact_geometry=None, task_weight_matrix=None) -> BatchResult:
-        """Host numpy buffers in, host numpy buffers out (H2D + kernels + D2H inside the call)."""
+                   contact_geometry=None, task_weight_matrix=None, time=None) -> BatchResult:
+        """Host numpy buffers in, host numpy buffers out (H2D + kernels + D2H inside the call).  `time`: the functor's t
+        (scalar or [B]) for controllers with device-side SE3PDControllers."""
         h = self.h
         h.sync_defaults()
         q, v, desired, cw, cm, B = _prep_host_inputs(h, q, v, desired, contact_weight, contact_maxnormalforce)
@@ -447,7 +501,8 @@ class DeviceController:
         else:
             tw, cg, twm = _prep_tick_parameters(h, task_weight, contact_geometry, B, task_weight_matrix)
         res = _alloc_out(h, B)
-        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg, task_weight_matrix=twm), _batch_out(res)
+        bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg, task_weight_matrix=twm,
+                            time=_prep_time(time, B)), _batch_out(res)
         check(self.lib, self.lib.qpc_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo), C.c_int32(HOST_PTRS),
                                                  None), "qpc_solve_batch")
         return res
@@ -505,7 +560,7 @@ class DeviceController:
                                                  C.c_int32(DEVICE_PTRS), C.c_void_p(stream)), "qpc_solve_batch")
 
     def assemble_host(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None, task_weight=None,
-                      contact_geometry=None):
+                      contact_geometry=None, time=None):
         """Stage-level entry point: the condensed QP of every instance."""
         h = self.h
         h.sync_defaults()
@@ -514,7 +569,7 @@ class DeviceController:
         out = dict(P=np.zeros((B, h.n, h.n)), q=np.zeros((B, h.n)), G=np.zeros((B, h.mg, h.n)),
                    lg=np.zeros((B, h.mg)), ug=np.zeros((B, h.mg)), lb=np.zeros((B, h.nbox)), ub=np.zeros((B, h.nbox)),
                    desired=np.zeros((B, h.ndes)))
-        bi = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg)
+        bi = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg, time=_prep_time(time, B))
         check(self.lib, self.lib.qpc_assemble_batch(h.ctrl, C.c_int64(B), C.byref(bi), _p(out["P"]), _p(out["q"]),
                                                     _p(out["G"]), _p(out["lg"]), _p(out["ug"]), _p(out["lb"]),
                                                     _p(out["ub"]), _p(out["desired"]), C.c_int32(HOST_PTRS), None),

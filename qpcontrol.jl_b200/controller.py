@@ -94,6 +94,19 @@ class MomentumBasedController:
         self.program.events.append(("contact", len(self.program.contacts) - 1))
         return point
 
+    def bind_se3pd(self, task: int, controller) -> int:
+        """Lets the device evaluate `setdesired!(task, controller(t, state))` every tick: `controller` is an
+        `SE3PDController` (se3pdcontroller.jl:1-18) whose reference is an `SE3Trajectory` of Interpolated / Constant /
+        Piecewise components, `task` the index `addtask` returned for the SpatialAccelerationTask it drives (expressed
+        in the controller's body frame).  The tick's `time` argument is the functor's t; trajectory and gains may be
+        replaced between ticks (they are Refs in the reference).  Returns the binding's index."""
+        self._check_open()
+        from .program import SE3PDSpec, SpatialAccelerationTask
+        if not (0 <= task < len(self.program.tasks)) or not isinstance(self.program.tasks[task].task, SpatialAccelerationTask):
+            raise ValueError("bind_se3pd: `task` must be the index of a SpatialAccelerationTask")
+        self.program.se3pd.append(SE3PDSpec(int(task), controller))
+        return len(self.program.se3pd) - 1
+
     # -- device side ---------------------------------------------------------------------------------------------
     def finalize(self):
         """`initialize!` (momentum.jl:150-156): freezes the program and builds the device controller."""
@@ -103,16 +116,18 @@ class MomentumBasedController:
         return self._dev
 
     def __call__(self, q, v, desired=None, contact_weight=None, contact_maxnormalforce=None,
-                 check: bool = True, task_weight=None, contact_geometry=None, task_weight_matrix=None) -> BatchResult:
+                 check: bool = True, task_weight=None, contact_geometry=None, task_weight_matrix=None,
+                 time=None) -> BatchResult:
         """The control tick for B instances.  `desired` [B, ndes] (task order) overrides the tasks' `setdesired!`
         values; contact arrays [B, ncontacts] override the ContactPoint fields per instance; `task_weight`
         [B, ntasks] and `contact_geometry` [B, ncontacts, 7] = (position, normal, mu) are the reference's
         Parameter-valued task weights and contact frames (momentum.jl:107-110, contacts.jl:39,53-61);
         `task_weight_matrix` [B, sum dim^2] are Parameter-valued MATRIX weights (momentum.jl:113-117): the dim x dim
-        matrices (row-major) of the matrix-weighted tasks, concatenated in addtask! order."""
+        matrices (row-major) of the matrix-weighted tasks, concatenated in addtask! order.  `time` (scalar or [B]) is
+        the functor's t, read by the SE3PDControllers bound with `bind_se3pd`."""
         dev = self.finalize()
         res = dev.solve_host(q, v, desired, contact_weight, contact_maxnormalforce, task_weight, contact_geometry,
-                             task_weight_matrix)
+                             task_weight_matrix, time)
         if check:
             checkstatus(res.status)
         return res
@@ -136,11 +151,11 @@ class MomentumBasedController:
         return q, v, res
 
     def simulate(self, q, v, dt: float, nsteps: int, desired=None, contact_weight=None, contact_maxnormalforce=None,
-                 check: bool = True):
+                 check: bool = True, time=None):
         """Closed loop of `nsteps` control ticks at period `dt` for B instances, on the device
         (notebooks/Standing controller.ipynb:202-214 batched; see qpc_step_batch).  Returns (q, v, last BatchResult)."""
         dev = self.finalize()
-        q, v, res = dev.step_host(q, v, dt, nsteps, desired, contact_weight, contact_maxnormalforce)
+        q, v, res = dev.step_host(q, v, dt, nsteps, desired, contact_weight, contact_maxnormalforce, time=time)
         if check:
             checkstatus(res.status)
         return q, v, res

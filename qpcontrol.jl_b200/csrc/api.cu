@@ -23,7 +23,8 @@ struct DeviceBuffers {
   double *tau = nullptr, *vdot = nullptr, *wrench = nullptr, *res = nullptr;
   int *status = nullptr, *iters = nullptr;
   double* twm = nullptr;  // staging of per-tick matrix weights
-  long long capB = 0, cap_desired = 0, cap_contact = 0, cap_tw = 0, cap_cg = 0, cap_twm = 0;
+  double* time = nullptr; // staging of the controller times (SE3PDControllers)
+  long long capB = 0, cap_desired = 0, cap_contact = 0, cap_tw = 0, cap_cg = 0, cap_twm = 0, cap_time = 0;
 };
 struct Backend {
   bool dirty = false;
@@ -84,6 +85,7 @@ qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb,
     kin_forward(pg, s);
     kin_composite(pg, s);
     kin_standing(pg, s);
+    kin_se3pd(pg, io, inst, s);
     kin_contacts(pg, s);
     const int n = pg->n, mg = pg->mg, nbx = pg->nbx;
     kin_assemble(pg, s, qb.P + inst * n * n, qb.qv + inst * n, qb.G + inst * mg * n, qb.lg + inst * mg,
@@ -607,6 +609,15 @@ static int ensure_twm(qpc_controller* c, long long B, long long stride) {
   return QPC_OK;
 }
 
+static int ensure_time(qpc_controller* c, long long B) {
+  DeviceBuffers& b = c->be.buf;
+  if (B > b.cap_time) {
+    CUDA_TRY(grow(b.time, B));
+    b.cap_time = B;
+  }
+  return QPC_OK;
+}
+
 static QpBuffers qp_view(const DeviceBuffers& b) {
   QpBuffers q;
   q.P = b.P;
@@ -815,7 +826,7 @@ void qpc_controller_destroy(qpc_controller* c) {
     cudaSetDevice(c->be.device);
     DeviceBuffers& b = c->be.buf;
     void* ptrs[] = {b.P, b.qv, b.G, b.lg, b.ug, b.lb, b.ub, b.des, b.x, b.y, b.q, b.v, b.desired, b.cw,
-                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.ksave, b.anchor, b.tw, b.cg, b.twm, c->be.d_fb_list, c->be.d_fb_count};
+                    b.cm, b.tau, b.vdot, b.wrench, b.res, b.status, b.iters, c->be.d_prog, c->be.d_nfac, b.rho, b.ksave, b.anchor, b.tw, b.cg, b.twm, b.time, c->be.d_fb_list, c->be.d_fb_count};
     for (int i = 0; i < 4; i++)
       if (c->be.ev[i]) cudaEventDestroy(c->be.ev[i]);
     for (void* p : ptrs)
@@ -856,9 +867,20 @@ static int stage_tick_parameters(qpc_controller* c, long long B, const qpc_batch
                                  BatchIO& io, cudaStream_t s) {
   const DevProgram& p = c->prog;
   DeviceBuffers& b = c->be.buf;
-  io.tweight = io.cgeom = io.twmat = nullptr;
-  io.tweight_stride = io.cgeom_stride = io.twmat_stride = 0;
+  io.tweight = io.cgeom = io.twmat = io.time = nullptr;
+  io.tweight_stride = io.cgeom_stride = io.twmat_stride = io.time_stride = 0;
   if (!in) return QPC_OK;
+  if (in->time && p.nse3 > 0) {  // 8 bytes per instance: copied whole, ahead of the chunks
+    io.time_stride = in->time_stride ? 1 : 0;
+    io.time = in->time;
+    if (host) {
+      const long long cnt = io.time_stride ? B : 1;
+      int rc = ensure_time(c, cnt);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemcpyAsync(b.time, in->time, sizeof(double) * (size_t)cnt, cudaMemcpyHostToDevice, s));
+      io.time = b.time;
+    }
+  }
   if (in->task_weight_matrix && p.nwmat > 0) {
     io.twmat_stride = in->task_weight_matrix_stride;
     io.twmat = in->task_weight_matrix;
@@ -998,6 +1020,7 @@ int qpc_solve_batch_multi(qpc_controller* const* ctrls, int32_t nctrl, int64_t B
     if (i2.task_weight) i2.task_weight += lo * i2.task_weight_stride;
     if (i2.contact_geometry) i2.contact_geometry += lo * i2.contact_geometry_stride;
     if (i2.task_weight_matrix) i2.task_weight_matrix += lo * i2.task_weight_matrix_stride;
+    if (i2.time && i2.time_stride) i2.time += lo;
     if (o2.tau) o2.tau += lo * p.nv;
     if (o2.vdot) o2.vdot += lo * p.nv;
     if (o2.wrench) o2.wrench += lo * p.ncontacts * 6;
@@ -1233,6 +1256,7 @@ static int step_impl(qpc_controller* c, int64_t B, double* q, double* v, const q
   }
   double* anchor = plant ? b.anchor : nullptr;  // persists across calls; qpc_reset_warm_start clears it
   for (int k = 0; k < nsteps; k++) {
+    io.time_offset = k * dt;  // the functor's t (se3pdcontroller.jl:13): qpc_batch_in.time is the time of the first tick
     rc = run_tick(c, B, io, plant ? tau_dev : o.tau, vdot, o.wrench, status, o.iters, o.residuals, o.factorizations, s);
     if (rc) return rc;
     if (!plant) {

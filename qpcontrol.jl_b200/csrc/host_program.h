@@ -37,6 +37,12 @@ struct HostStanding {
   double com_kp = 0, com_kd = 0, pelvis_kp = 0, pelvis_kd = 0, comref[3] = {0, 0, 0};
 };
 
+struct HostSE3PD {
+  int task, base, body;
+  double K[36];
+  DevTraj ang, lin;
+};
+
 struct HostController {
   const HostMechanism* mech = nullptr;
   int N = 4, floating = -1;
@@ -44,6 +50,7 @@ struct HostController {
   std::vector<HostContact> contacts;
   std::vector<double> reg;
   HostStanding standing;
+  std::vector<HostSE3PD> se3;
   Settings settings;
   int ndes = 0;
 };
@@ -288,6 +295,18 @@ inline std::string compile_program(const HostController& hc, DevProgram& p) {
     p.st_pelvis_kp = st.pelvis_kp;
     p.st_pelvis_kd = st.pelvis_kd;
     for (int i = 0; i < 3; i++) p.st_comref[i] = st.comref[i];
+  }
+  p.nse3 = (int)hc.se3.size();
+  for (int i = 0; i < p.nse3; i++) {
+    const HostSE3PD& h = hc.se3[i];
+    DevSE3PD& d = p.se3[i];
+    d.body = h.body;
+    d.base = h.base;
+    d.task = h.task;
+    d.des_off = hc.tasks[h.task].des_off;
+    std::memcpy(d.K, h.K, sizeof(d.K));
+    d.ang = h.ang;
+    d.lin = h.lin;
   }
   p.settings = hc.settings;
   return "";

@@ -307,6 +307,101 @@ QPC_DEV void kin_standing(const DevProgram* __restrict__ pg, KinSmem& s) {
   QPC_SYNC();
 }
 
+// ---- SE3PDController on the device (reference src/lowlevel/se3pdcontroller.jl:13-18) ---------------------------------------
+// One `Interpolated` / `Piecewise` trajectory with two derivatives (interpolated.jl:19-60, piecewise.jl:25-40).
+// rotation: y[4] quaternion, d1 / d2 angular velocity / acceleration (Lie derivative, interpolated.jl:75-82);
+// vector: y[0..2], d1, d2.
+QPC_DEV void traj_eval(const DevTraj& tr, double x, bool rotation, double* y, V3& d1, V3& d2) {
+  int k = 0;
+  if (tr.piecewise) {
+    const double xc = fmin(fmax(x, tr.seg[0].brk), tr.brk_end);
+    for (int i = 1; i < tr.nseg; i++)
+      if (tr.seg[i].brk <= xc) k = i;
+    x = xc - tr.seg[k].brk;
+  }
+  const DevInterp& g = tr.seg[k];
+  const double dx = g.xf - g.x0;
+  double th = (x - g.x0) / dx, dth = 1.0 / dx;
+  if (th <= 0.0) {
+    th = 0.0;
+    dth = 0.0;
+  } else if (th >= 1.0) {
+    th = 1.0;
+    dth = 0.0;
+  }
+  double al = th, al1 = 1.0, al2 = 0.0;
+  if (g.nc > 0) {  // Horner on the polynomial and its first two derivatives
+    al = al1 = al2 = 0.0;
+    for (int i = g.nc - 1; i >= 0; i--) {
+      al2 = al2 * th + 2.0 * al1;
+      al1 = al1 * th + al;
+      al = al * th + g.c[i];
+    }
+  }
+  const double a1 = al1 * dth, a2 = al2 * dth * dth;
+  const V3 ax = ld3(g.dy);
+  if (rotation) {
+    double sh, ch;
+    sincos(0.5 * al * g.angle, &sh, &ch);
+    const double w1 = g.y0[0], x1 = g.y0[1], y1 = g.y0[2], z1 = g.y0[3];
+    const double x2 = sh * ax.x, y2 = sh * ax.y, z2 = sh * ax.z;
+    y[0] = w1 * ch - x1 * x2 - y1 * y2 - z1 * z2;
+    y[1] = w1 * x2 + x1 * ch + y1 * z2 - z1 * y2;
+    y[2] = w1 * y2 - x1 * z2 + y1 * ch + z1 * x2;
+    y[3] = w1 * z2 + x1 * y2 - y1 * x2 + z1 * ch;
+    d1 = (a1 * g.angle) * ax;
+    d2 = (a2 * g.angle) * ax;
+  } else {
+    st3(y, ld3(g.y0) + al * ax);
+    d1 = a1 * ax;
+    d2 = a2 * ax;
+  }
+}
+QPC_DEV V3 mat3_mul(const double* M, V3 v) { return rot(M, v); }
+
+// Desired spatial acceleration of every SE3PDController at time t: Tdref + pd(gains, H, Href, T, Tref), double-geodesic
+// PD in the body frame (RigidBodyDynamics.PDControl, restated in qpcontrol.jl_b200/se3pd.py: pd_se3), written over the
+// desired of the SpatialAccelerationTask the controller drives.  Runs after kin_forward (transforms and twists).
+// (not inlined, scalar arguments only: keeps its registers out of the assembly kernels, which run it for few programs)
+static QPC_DEVN void kin_se3pd_eval(const DevProgram* __restrict__ pg, double t, const double* Hs, const double* TWs, double* des) {
+  KinSmem s;
+  s.H = const_cast<double*>(Hs);
+  s.TW = const_cast<double*>(TWs);
+  s.des = des;
+  for (int c = QPC_TID; c < pg->nse3; c += QPC_NT) {
+    const DevSE3PD& sc = pg->se3[c];
+    // reference pose, twist and spatial acceleration in the desired body frame (se3.jl:8-27)
+    double quat[4], pdes[3], Rd[9];
+    V3 w_base, wd_base, pd1, pd2;
+    traj_eval(sc.ang, t, true, quat, w_base, wd_base);
+    traj_eval(sc.lin, t, false, pdes, pd1, pd2);
+    quat_to_rot(quat[0], quat[1], quat[2], quat[3], Rd);
+    const V3 w_des = rot_t(Rd, w_base), nu_des = rot_t(Rd, pd1);
+    const V3 wd_des = rot_t(Rd, wd_base), nud_des = rot_t(Rd, pd2) + cross(w_des, nu_des);
+    // actual pose of body in base and relative twist in the body frame (se3pdcontroller.jl:15-16)
+    const Xf Hb = body_to_root(s, sc.body), Ha = body_to_root(s, sc.base);
+    const Xf H = xf_mul(xf_inv(Ha), Hb);
+    const S6 T = xmotion(xf_inv(Hb), body_twist(s, sc.body) - body_twist(s, sc.base));
+    // error pose e = inv(x_des) * x and the reference twist re-expressed in the body frame
+    double Re[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Re[3 * i + j] = Rd[i] * H.R[j] + Rd[3 + i] * H.R[3 + j] + Rd[6 + i] * H.R[6 + j];
+    const V3 pe = rot_t(Rd, H.p - ld3(pdes));
+    const V3 pe_b = rot_t(Re, pe);
+    const V3 w_des_b = rot_t(Re, w_des);
+    const V3 nu_des_b = rot_t(Re, nu_des) + cross(-pe_b, w_des_b);
+    const V3 ang = -mat3_mul(sc.K, rot_to_rotvec(Re)) - mat3_mul(sc.K + 9, T.w - w_des_b);
+    const V3 lin = -mat3_mul(sc.K + 18, pe_b) - mat3_mul(sc.K + 27, T.v - nu_des_b);
+    st3(s.des + sc.des_off, wd_des + ang);
+    st3(s.des + sc.des_off + 3, nud_des + lin);
+  }
+}
+QPC_DEV void kin_se3pd(const DevProgram* __restrict__ pg, const BatchIO& io, long long inst, KinSmem& s) {
+  if (!pg->nse3) return;
+  kin_se3pd_eval(pg, (io.time ? io.time[inst * io.time_stride] : 0.0) + io.time_offset, s.H, s.TW, s.des);
+  QPC_SYNC();
+}
+
 // contact frames and unit-generator wrenches: toroot = transform_to_root(body) * z_up (contacts.jl:61);
 // generator g of contact c produces the world wrench (p x (R b_g); R b_g)  (contacts.jl:63,66,67)
 QPC_DEV void kin_contacts(const DevProgram* __restrict__ pg, KinSmem& s) {

@@ -25,6 +25,7 @@ qpc_assemble_warp_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffer
     kin_forward(pg, s);
     kin_composite(pg, s);
     kin_standing(pg, s);
+    kin_se3pd(pg, io, inst, s);
     kin_contacts(pg, s);
     const int n = pg->n, mg = pg->mg, nbx = pg->nbx;
     kin_assemble(pg, s, qb.P + inst * n * n, qb.qv + inst * n, qb.G + inst * mg * n, qb.lg + inst * mg,

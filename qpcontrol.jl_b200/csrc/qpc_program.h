@@ -14,6 +14,8 @@
 #define QPC_MAXPATH 512 // total path entries over all tasks
 #define QPC_MAXDES 160  // total desired dimension
 #define QPC_MAXW 256    // matrix-weight storage (doubles)
+#define QPC_MAXSE3 4    // SE3PDControllers evaluated on the device
+#define QPC_MAXSEG 6    // Interpolated pieces of one (Piecewise) trajectory
 
 namespace qpc {
 
@@ -39,6 +41,27 @@ struct DevContact {
   double B[3 * QPC_MAXN];          // forcebasis(mu, N), 3 x N row-major (contacts.jl:16-23)
   double BtB[QPC_MAXN * QPC_MAXN]; // B'B
   double maxrho_factor;            // 1 / (N sqrt(mu^2 + 1))  (contacts.jl:57)
+};
+
+// One `Interpolated` piece (reference src/trajectories/interpolated.jl:1-60) of a `Piecewise` trajectory
+// (piecewise.jl:1-40): active from break `brk`, evaluated at x - brk.  Rotation: y0 = quaternion (w, x, y, z), dy = unit
+// axis of y0 \ yf, angle its rotation angle (interpolated.jl:75-82); vector: y0[0..2], dy = yf - y0.  c = ascending
+// coefficients of the polynomial interpolator alpha(theta), nc = 0 for the identity.
+struct DevInterp {
+  double brk, x0, xf, y0[4], dy[3], angle, c[6];
+  int nc, pad;
+};
+struct DevTraj {
+  int nseg, piecewise;  // not piecewise: seg[0] evaluated at x itself
+  double brk_end;       // last break of the Piecewise (clamp range [seg[0].brk, brk_end])
+  DevInterp seg[QPC_MAXSEG];
+};
+// SE3PDController (reference src/lowlevel/se3pdcontroller.jl:1-18) driving the desired of one SpatialAccelerationTask:
+// SE3Trajectory (src/trajectories/se3.jl:1-27) of `body` in `base` + SE3PDGains (3x3 row-major: K_ang, D_ang, K_lin, D_lin)
+struct DevSE3PD {
+  int body, base, des_off, task;
+  double K[36];
+  DevTraj ang, lin;
 };
 
 struct DevProgram {
@@ -73,6 +96,9 @@ struct DevProgram {
   int st_jq[QPC_MAXV], st_jv[QPC_MAXV], st_jdes[QPC_MAXV];
   double st_kp[QPC_MAXV], st_kd[QPC_MAXV], st_ref[QPC_MAXV];
   double st_com_kp, st_com_kd, st_pelvis_kp, st_pelvis_kd, st_comref[3];
+  // ---- SE3PDControllers evaluated in the assembly prologue (se3pdcontroller.jl:13-18) ------------------------------
+  int nse3;
+  DevSE3PD se3[QPC_MAXSE3];
   Settings settings;
 };
 
@@ -86,6 +112,9 @@ struct BatchIO {
   long long tweight_stride = 0, cgeom_stride = 0;
   const double* twmat = nullptr;    // [B][twmat_stride] matrix weights of the matrix-weighted tasks, Wbuf layout (momentum.jl:113-117)
   long long twmat_stride = 0;
+  const double* time = nullptr;     // controller time t of the tick: [B] (time_stride 1) or one value (time_stride 0)
+  long long time_stride = 0;
+  double time_offset = 0.0;         // added to the time: k * dt at tick k of the closed loops (qpc_step_batch / qpc_simulate_batch)
 };
 
 // the condensed QP of every instance, as written by the assembly kernel and consumed by the ADMM kernel

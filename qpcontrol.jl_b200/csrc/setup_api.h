@@ -261,6 +261,92 @@ int qpc_standing_setup(qpc_controller* c, int32_t linmom_task, int32_t pelvis_ta
   return QPC_OK;
 }
 
+// ---- SE3PDController on the device (se3pdcontroller.jl:1-18) ------------------------------------------------------------
+static const char* fill_trajectory(qpc::DevTraj& tr, int32_t n, const qpc_interp_piece* pcs, int32_t piecewise,
+                                   double break_end, bool rotation) {
+  if (n < 1 || n > QPC_MAXSEG || !pcs) return "between 1 and QPC_MAX_PIECES pieces per trajectory";
+  if (!piecewise && n != 1) return "a trajectory that is not piecewise has exactly one piece";
+  std::memset(&tr, 0, sizeof(tr));
+  tr.nseg = n;
+  tr.piecewise = piecewise ? 1 : 0;
+  tr.brk_end = break_end;
+  for (int i = 0; i < n; i++) {
+    const qpc_interp_piece& s = pcs[i];
+    qpc::DevInterp& d = tr.seg[i];
+    if (!(s.xf > s.x0) || !std::isfinite(s.x0) || !std::isfinite(s.xf)) return "piece with xf <= x0";
+    if (s.ncoeffs < 0 || s.ncoeffs > 6) return "interpolator polynomials have at most 6 coefficients";
+    if (piecewise && ((i > 0 && !(s.break_start >= pcs[i - 1].break_start)) || !(break_end >= s.break_start)))
+      return "Piecewise breaks must be sorted";
+    if (rotation) {
+      const double nq = s.y0[0] * s.y0[0] + s.y0[1] * s.y0[1] + s.y0[2] * s.y0[2] + s.y0[3] * s.y0[3];
+      const double na = s.dy[0] * s.dy[0] + s.dy[1] * s.dy[1] + s.dy[2] * s.dy[2];
+      if (std::fabs(nq - 1.0) > 1e-9 || std::fabs(na - 1.0) > 1e-9) return "rotation pieces need a unit quaternion and a unit axis";
+    }
+    d.brk = piecewise ? s.break_start : 0.0;
+    d.x0 = s.x0;
+    d.xf = s.xf;
+    for (int k = 0; k < 4; k++) d.y0[k] = s.y0[k];
+    for (int k = 0; k < 3; k++) d.dy[k] = s.dy[k];
+    d.angle = s.angle;
+    for (int k = 0; k < 6; k++) d.c[k] = k < s.ncoeffs ? s.coeffs[k] : 0.0;
+    d.nc = s.ncoeffs;
+  }
+  return nullptr;
+}
+
+int qpc_add_se3pd(qpc_controller* c, int32_t task, int32_t base_body, int32_t body, const double gains[36],
+                  int32_t n_angular, const qpc_interp_piece* angular, int32_t angular_piecewise, double angular_break_end,
+                  int32_t n_linear, const qpc_interp_piece* linear, int32_t linear_piecewise, double linear_break_end) {
+  QPC_CHECK_OPEN(c);
+  const qpc::HostMechanism& m = *c->hc.mech;
+  if (task < 0 || task >= (int)c->hc.tasks.size() || c->hc.tasks[task].kind != QPC_TASK_SPATIAL)
+    return qpc_fail(QPC_ERR_ARG, "qpc_add_se3pd: `task` must be a SpatialAccelerationTask added before");
+  if (body < 0 || body >= m.nb || base_body < -1 || base_body >= m.nb) return qpc_fail(QPC_ERR_ARG, "qpc_add_se3pd: body out of range");
+  if (!gains) return qpc_fail(QPC_ERR_ARG, "qpc_add_se3pd: null gains");
+  if ((int)c->hc.se3.size() >= QPC_MAXSE3) return qpc_fail(QPC_ERR_LIMIT, "too many SE3PDControllers");
+  for (auto& o : c->hc.se3)
+    if (o.task == task) return qpc_fail(QPC_ERR_ARG, "qpc_add_se3pd: the task is already driven by an SE3PDController");
+  qpc::HostSE3PD h;
+  h.task = task;
+  h.base = base_body;
+  h.body = body;
+  std::memcpy(h.K, gains, sizeof(h.K));
+  if (const char* e = fill_trajectory(h.ang, n_angular, angular, angular_piecewise, angular_break_end, true))
+    return qpc_fail(QPC_ERR_ARG, std::string("qpc_add_se3pd: angular: ") + e);
+  if (const char* e = fill_trajectory(h.lin, n_linear, linear, linear_piecewise, linear_break_end, false))
+    return qpc_fail(QPC_ERR_ARG, std::string("qpc_add_se3pd: linear: ") + e);
+  c->hc.se3.push_back(h);
+  return (int)c->hc.se3.size() - 1;
+}
+
+int qpc_se3pd_update(qpc_controller* c, int32_t se3pd, const double* gains,
+                     int32_t n_angular, const qpc_interp_piece* angular, int32_t angular_piecewise, double angular_break_end,
+                     int32_t n_linear, const qpc_interp_piece* linear, int32_t linear_piecewise, double linear_break_end) {
+  if (!c || se3pd < 0 || se3pd >= (int)c->hc.se3.size()) return qpc_fail(QPC_ERR_ARG, "qpc_se3pd_update: bad index");
+  std::unique_lock<std::mutex> lock(c->be.mu, std::defer_lock);
+  if (c->finalized) lock.lock();
+  qpc::HostSE3PD h = c->hc.se3[se3pd];
+  if (gains) std::memcpy(h.K, gains, sizeof(h.K));
+  if (angular)
+    if (const char* e = fill_trajectory(h.ang, n_angular, angular, angular_piecewise, angular_break_end, true))
+      return qpc_fail(QPC_ERR_ARG, std::string("qpc_se3pd_update: angular: ") + e);
+  if (linear)
+    if (const char* e = fill_trajectory(h.lin, n_linear, linear, linear_piecewise, linear_break_end, false))
+      return qpc_fail(QPC_ERR_ARG, std::string("qpc_se3pd_update: linear: ") + e);
+  const qpc::HostSE3PD& old = c->hc.se3[se3pd];
+  const bool changed = std::memcmp(old.K, h.K, sizeof(h.K)) || std::memcmp(&old.ang, &h.ang, sizeof(h.ang)) ||
+                       std::memcmp(&old.lin, &h.lin, sizeof(h.lin));
+  c->hc.se3[se3pd] = h;
+  if (c->finalized && changed) {
+    qpc::DevSE3PD& d = c->prog.se3[se3pd];
+    std::memcpy(d.K, h.K, sizeof(d.K));
+    d.ang = h.ang;
+    d.lin = h.lin;
+    c->be.dirty = true;
+  }
+  return QPC_OK;
+}
+
 int qpc_set_settings(qpc_controller* c, const qpc_settings* s) {
   if (!c || !s) return qpc_fail(QPC_ERR_ARG, "null argument");
   std::unique_lock<std::mutex> lock(c->be.mu, std::defer_lock);

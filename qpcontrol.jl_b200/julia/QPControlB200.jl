@@ -17,7 +17,8 @@ import RigidBodyDynamics: Mechanism, RigidBody, Joint, bodies, joints, tree_join
 export MomentumBasedController, StandingController, ContactPoint, OSQPSettings, QPSolveFailure,
     SpatialAccelerationTask, AngularAccelerationTask, LinearAccelerationTask, PointAccelerationTask,
     JointAccelerationTask, MomentumRateTask, LinearMomentumRateTask,
-    addtask!, addcontact!, regularize!, setdesired!, disable!, checkstatus, warmstart!, resetwarmstart!, simulate!
+    addtask!, addcontact!, regularize!, setdesired!, disable!, checkstatus, warmstart!, resetwarmstart!, simulate!,
+    simulateplant!, bindse3pd!, InterpPiece, rotationpiece, vectorpiece
 
 const LIB = Ref{String}(get(ENV, "QPCONTROL_B200_LIB", "libqpcontrol_b200"))
 
@@ -225,11 +226,14 @@ struct qpc_batch_in
     task_weight::Ptr{Cdouble}; task_weight_stride::Int64            # per-tick Parameter weights (momentum.jl:107-110)
     contact_geometry::Ptr{Cdouble}; contact_geometry_stride::Int64  # per-tick position / normal / mu (contacts.jl:39)
     task_weight_matrix::Ptr{Cdouble}; task_weight_matrix_stride::Int64  # per-tick matrix weights (momentum.jl:113-117)
+    time::Ptr{Cdouble}; time_stride::Int64                          # the functor's t (se3pdcontroller.jl:13); 0 = one value
 end
 qpc_batch_in(q, v, desired, dstride, cw, cm, cstride) =
-    qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, C_NULL, 0, C_NULL, 0, C_NULL, 0)
+    qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, C_NULL, 0, C_NULL, 0, C_NULL, 0, C_NULL, 0)
 qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, tw, twstride, cg, cgstride) =
-    qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, tw, twstride, cg, cgstride, C_NULL, 0)
+    qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, tw, twstride, cg, cgstride, C_NULL, 0, C_NULL, 0)
+qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, tw, twstride, cg, cgstride, time::Ptr{Cdouble}) =
+    qpc_batch_in(q, v, desired, dstride, cw, cm, cstride, tw, twstride, cg, cgstride, C_NULL, 0, time, 0)
 struct qpc_batch_out
     tau::Ptr{Cdouble}; vdot::Ptr{Cdouble}; wrench::Ptr{Cdouble}; status::Ptr{Int32}; iters::Ptr{Int32}
     residuals::Ptr{Cdouble}; factorizations::Ptr{Int32}
@@ -250,13 +254,14 @@ function (c::MomentumBasedController)(tau::Matrix{Float64}, t::Number, q::Matrix
     B = size(q, 2)
     nc = length(c.contacts)
     vdot = similar(v); wrench = zeros(6, nc, B); status = zeros(Int32, B); iters = zeros(Int32, B); res = zeros(2, B)
-    GC.@preserve tau q v vdot wrench status iters res maxnormalforce weight taskweight contactgeometry begin
+    tref = Float64[t]   # the functor's t: read by the device-side SE3PDControllers (bindse3pd!)
+    GC.@preserve tau q v vdot wrench status iters res maxnormalforce weight taskweight contactgeometry tref begin
         bin = qpc_batch_in(pointer(q), pointer(v), C_NULL, 0,
                            weight === nothing ? C_NULL : pointer(weight),
                            maxnormalforce === nothing ? C_NULL : pointer(maxnormalforce), nc,
                            taskweight === nothing ? C_NULL : pointer(taskweight),
                            taskweight === nothing ? 0 : size(taskweight, 1),
-                           contactgeometry === nothing ? C_NULL : pointer(contactgeometry), 7 * nc)
+                           contactgeometry === nothing ? C_NULL : pointer(contactgeometry), 7 * nc, pointer(tref))
         bout = qpc_batch_out(pointer(tau), pointer(vdot), pointer(wrench), pointer(status), pointer(iters),
                              pointer(res), C_NULL)
         QPControlB200.check(ccall((:qpc_solve_batch, LIB[]), Cint,
@@ -265,6 +270,44 @@ function (c::MomentumBasedController)(tau::Matrix{Float64}, t::Number, q::Matrix
     end
     check && checkstatus(status)
     vdot, wrench, status
+end
+
+# ---- SE3PDController on the device (SURVEY.md 8(f) rank 3; reference src/lowlevel/se3pdcontroller.jl:1-18) ---------------
+# One Interpolated piece of an SE3Trajectory component (interpolated.jl:1-60), mirror of qpc_interp_piece.
+struct InterpPiece
+    break_start::Cdouble; x0::Cdouble; xf::Cdouble
+    y0::NTuple{4,Cdouble}; dy::NTuple{3,Cdouble}; angle::Cdouble
+    coeffs::NTuple{6,Cdouble}; ncoeffs::Int32; reserved::Int32
+end
+_coeffs(c) = (ntuple(i -> i <= length(c) ? Float64(c[i]) : 0.0, 6), Int32(length(c)))
+# rotation piece from quaternions (w, x, y, z): axis / angle of y0 \ yf (interpolated.jl:75-78)
+function rotationpiece(x0, xf, y0::NTuple{4,Float64}, yf::NTuple{4,Float64}; coeffs=Float64[], break_start=0.0)
+    w1, x1, y1, z1 = y0; w2, x2, y2, z2 = yf
+    d = (w1 * w2 + x1 * x2 + y1 * y2 + z1 * z2, w1 * x2 - x1 * w2 - y1 * z2 + z1 * y2,
+         w1 * y2 + x1 * z2 - y1 * w2 - z1 * x2, w1 * z2 - x1 * y2 + y1 * x2 - z1 * w2)      # conj(y0) * yf
+    d = d[1] < 0 ? map(-, d) : d
+    s = sqrt(d[2]^2 + d[3]^2 + d[4]^2)
+    axis = s > 0 ? (d[2] / s, d[3] / s, d[4] / s) : (1.0, 0.0, 0.0)
+    c, n = _coeffs(coeffs)
+    InterpPiece(break_start, x0, xf, y0, axis, 2atan(s, d[1]), c, n, 0)
+end
+function vectorpiece(x0, xf, y0, yf; coeffs=Float64[], break_start=0.0)
+    c, n = _coeffs(coeffs)
+    InterpPiece(break_start, x0, xf, (y0[1], y0[2], y0[3], 0.0), (yf[1] - y0[1], yf[2] - y0[2], yf[3] - y0[3]), 0.0, c, n, 0)
+end
+# SE3PDController(base, body, trajectory, weight, gains) bound to the SpatialAccelerationTask `task` it drives: from then on
+# the device evaluates setdesired!(task, controller(t, state)) every tick.  gains: (K_ang, D_ang, K_lin, D_lin) 3x3 matrices.
+function bindse3pd!(c::MomentumBasedController, task::SpatialAccelerationTask, base::RigidBody, body::RigidBody,
+                    gains::NTuple{4,Matrix{Float64}}, angular::Vector{InterpPiece}, linear::Vector{InterpPiece};
+                    angular_break_end::Float64=NaN, linear_break_end::Float64=NaN)
+    K = vcat((vec(permutedims(g)) for g in gains)...)   # row-major 3x3 blocks
+    id = ccall((:qpc_add_se3pd, LIB[]), Cint,
+               (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Cdouble}, Int32, Ptr{InterpPiece}, Int32, Cdouble, Int32, Ptr{InterpPiece},
+                Int32, Cdouble), c.handle, task.index, bodyid(c, base), bodyid(c, body), K,
+               length(angular), angular, isnan(angular_break_end) ? 0 : 1, isnan(angular_break_end) ? 0.0 : angular_break_end,
+               length(linear), linear, isnan(linear_break_end) ? 0 : 1, isnan(linear_break_end) ? 0.0 : linear_break_end)
+    check(id, "qpc_add_se3pd")
+    id
 end
 
 # ---- sequential ticks (SURVEY.md 8(f) rank 1) -----------------------------------------------------------------------------

@@ -220,6 +220,13 @@ class StandingSpec:
 
 
 @dataclass
+class SE3PDSpec:
+    """An `SE3PDController` (se3pdcontroller.jl:1-11) bound to the SpatialAccelerationTask whose desired it produces."""
+    task: int
+    controller: object  # qpcontrol.jl_b200.se3pd.SE3PDController
+
+
+@dataclass
 class Program:
     """Everything `addtask!` / `addcontact!` / `regularize!` recorded, in call order (the order defines the lifted
     QP's variable and row order in the reference, momentum.jl:28,123 and contacts.jl:46-48)."""
@@ -232,6 +239,7 @@ class Program:
     contacts: List[ContactPoint] = field(default_factory=list)
     reg: Optional[np.ndarray] = None
     standing: Optional[StandingSpec] = None
+    se3pd: List[SE3PDSpec] = field(default_factory=list)
 
     def __post_init__(self):
         if self.reg is None:

@@ -29,9 +29,12 @@ from typing import Tuple, Union
 import numpy as np
 
 from .mechanism import PRISMATIC, QUAT_FLOATING, REVOLUTE, Mechanism
-from .trajectories import quat_to_rot
+from .trajectories import Constant, Interpolated, Piecewise, PointTrajectory, Polynomial, quat_to_rot
 
-__all__ = ["PDGains", "SE3PDGains", "pd", "pd_se3", "rotation_vector", "body_pose_and_twist", "SE3PDController"]
+__all__ = ["PDGains", "SE3PDGains", "pd", "pd_se3", "rotation_vector", "body_pose_and_twist", "SE3PDController",
+           "compile_trajectory", "gains_matrix"]
+
+MAX_PIECES = 6  # QPC_MAX_PIECES of include/qpcontrol_b200.h
 
 Gain = Union[float, np.ndarray]
 
@@ -200,3 +203,58 @@ class SE3PDController:
         twist_des = np.concatenate([np.broadcast_to(w_des, twist[:, :3].shape),
                                     np.broadcast_to(nu_des, twist[:, 3:].shape)], axis=-1)
         return feed_forward + pd_se3(self.gains, R, p, R_des, p_des, twist, twist_des)
+
+
+# ---- device form: what qpc_add_se3pd / qpc_se3pd_update take (include/qpcontrol_b200.h: qpc_interp_piece) -------------------
+def _gain3(g: Gain) -> np.ndarray:
+    g = np.asarray(g, dtype=np.float64)
+    if g.ndim == 0:
+        return float(g) * np.eye(3)
+    if g.ndim == 1:
+        return np.diag(g)
+    return g
+
+
+def gains_matrix(gains: SE3PDGains) -> np.ndarray:
+    """[4, 3, 3]: K_angular, D_angular, K_linear, D_linear (scalar and per-axis gains become diagonal matrices)."""
+    return np.ascontiguousarray(np.stack([_gain3(gains.angular.k), _gain3(gains.angular.d), _gain3(gains.linear.k),
+                                          _gain3(gains.linear.d)]))
+
+
+def _piece(f, rotation: bool, break_start: float) -> dict:
+    if isinstance(f, Constant):
+        y0 = np.asarray(f.value, dtype=np.float64).ravel()
+        return dict(break_start=break_start, x0=0.0, xf=1.0, y0=y0, dy=np.array([1.0, 0, 0]) if rotation else np.zeros(3),
+                    angle=0.0, coeffs=[])
+    if not isinstance(f, Interpolated):
+        raise TypeError("the device evaluates Interpolated / Constant trajectories and Piecewise lists of them; got "
+                        + type(f).__name__)
+    if not f.clamp:
+        raise ValueError("device trajectories are clamped to their range (Interpolated(..., clamp=True))")
+    if bool(f.rotation) != rotation:
+        raise ValueError("angular components interpolate rotations, linear components 3-vectors")
+    if f.interpolator is None:
+        coeffs = []
+    elif isinstance(f.interpolator, Polynomial):
+        coeffs = list(f.interpolator.coeffs)
+        if len(coeffs) > 6:
+            raise ValueError("interpolator polynomials have at most 6 coefficients (quintic)")
+    else:
+        raise TypeError("the interpolator must be None (identity) or a Polynomial")
+    if rotation:
+        return dict(break_start=break_start, x0=f.x0, xf=f.xf, y0=f.y0, dy=f.axis, angle=float(f.angle), coeffs=coeffs)
+    return dict(break_start=break_start, x0=f.x0, xf=f.xf, y0=f.y0, dy=f.yf - f.y0, angle=0.0, coeffs=coeffs)
+
+
+def compile_trajectory(traj, rotation: bool):
+    """(pieces, piecewise, break_end) of one component of an SE3Trajectory for the device tables."""
+    while isinstance(traj, PointTrajectory):  # Point / FreeVector wrappers only carry the frame
+        traj = traj.trajectory
+    if isinstance(traj, Piecewise):
+        if not traj.clamp:
+            raise ValueError("device trajectories are clamped to their range (Piecewise(..., clamp=True))")
+        if len(traj.subfunctions) > MAX_PIECES:
+            raise ValueError(f"at most {MAX_PIECES} pieces per trajectory")
+        return ([_piece(f, rotation, float(b)) for f, b in zip(traj.subfunctions, traj.breaks[:-1])], True,
+                float(traj.breaks[-1]))
+    return [_piece(traj, rotation, 0.0)], False, 0.0

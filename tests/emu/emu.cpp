@@ -45,6 +45,8 @@ static BatchIO make_io(const qpc_batch_in* in) {
   io.cgeom_stride = in->contact_geometry_stride;
   io.twmat = in->task_weight_matrix;
   io.twmat_stride = in->task_weight_matrix_stride;
+  io.time = in->time;
+  io.time_stride = in->time_stride ? 1 : 0;
   return io;
 }
 
@@ -62,6 +64,7 @@ int emu_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
       kin_forward(&p, s);
       kin_composite(&p, s);
       kin_standing(&p, s);
+      kin_se3pd(&p, io, i, s);
       kin_contacts(&p, s);
       kin_assemble(&p, s, P + i * p.n * p.n, qv + i * p.n, G + i * p.mg * p.n, lg + i * p.mg, ug + i * p.mg,
                    lb + i * p.nbx, ub + i * p.nbx);
@@ -138,6 +141,7 @@ int emu_solve_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const 
       kin_forward(&p, s);
       kin_composite(&p, s);
       kin_standing(&p, s);
+      kin_se3pd(&p, io, i, s);
       kin_contacts(&p, s);
       kin_assemble(&p, s, P.data(), qv.data(), G.data(), lg.data(), ug.data(), lb.data(), ub.data());
       int status = 1, iters = 0;
@@ -181,6 +185,7 @@ int emu_id_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, const dou
       kin_forward(&p, s);
       kin_composite(&p, s);
       kin_standing(&p, s);
+      kin_se3pd(&p, io, i, s);
       kin_contacts(&p, s);
       kin_inverse_dynamics(&p, s, x + i * p.n, vd.data(), wr.data(), tau.data());
       for (int k = 0; k < p.nv; k++) {

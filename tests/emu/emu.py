@@ -32,7 +32,7 @@ class EmuController:
         self.h = L.Handles(self.lib, program, 0)
 
     def solve(self, q, v, desired=None, cw=None, cm=None, task_weight=None, contact_geometry=None,
-              task_weight_matrix=None):
+              task_weight_matrix=None, time=None):
         h = self.h
         h.sync_defaults()
         q, v, desired, cw, cm, B = L._prep_host_inputs(h, q, v, desired, cw, cm)
@@ -43,7 +43,7 @@ class EmuController:
             tw, cg, twm = L._prep_tick_parameters(h, task_weight, contact_geometry, B, task_weight_matrix)
         res = L._alloc_out(h, B)
         bi, bo = h.batch_in(q, v, desired, cw, cm, task_weight=tw, contact_geometry=cg,
-                            task_weight_matrix=twm), L._batch_out(res)
+                            task_weight_matrix=twm, time=L._prep_time(time, B)), L._batch_out(res)
         L.check(self.lib, self.lib.emu_solve_batch(h.ctrl, C.c_int64(B), C.byref(bi), C.byref(bo)), "emu_solve_batch")
         return res
 
@@ -75,14 +75,14 @@ class EmuController:
                 "emu_forward_dynamics_batch")
         return vd, fc[:, :h.ncontacts]
 
-    def assemble(self, q, v, desired=None, cw=None, cm=None):
+    def assemble(self, q, v, desired=None, cw=None, cm=None, time=None):
         h = self.h
         h.sync_defaults()
         q, v, desired, cw, cm, B = L._prep_host_inputs(h, q, v, desired, cw, cm)
         out = dict(P=np.zeros((B, h.n, h.n)), q=np.zeros((B, h.n)), G=np.zeros((B, h.mg, h.n)),
                    lg=np.zeros((B, h.mg)), ug=np.zeros((B, h.mg)), lb=np.zeros((B, h.nbox)), ub=np.zeros((B, h.nbox)),
                    desired=np.zeros((B, h.ndes)))
-        bi = h.batch_in(q, v, desired, cw, cm)
+        bi = h.batch_in(q, v, desired, cw, cm, time=L._prep_time(time, B))
         p = L._p
         L.check(self.lib, self.lib.emu_assemble_batch(h.ctrl, C.c_int64(B), C.byref(bi), p(out["P"]), p(out["q"]),
                                                       p(out["G"]), p(out["lg"]), p(out["ug"]), p(out["lb"]),
