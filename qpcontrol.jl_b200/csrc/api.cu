@@ -76,6 +76,9 @@ constexpr int ADMM_BIG_THREADS = 512;
 constexpr int ADMM_BIG_SMEM = 100 * 1024;  // above this at most two CTAs fit an SM: run them with ADMM_BIG_THREADS
 constexpr int ID_THREADS = QPC_KIN_THREADS;
 
+// SE3: programs with device-side SE3PDControllers (kin_se3pd); a separate instantiation so that the evaluator's registers
+// stay out of the kernel every other program runs (one shared kernel cost the Atlas standing tick 0.18 ms in spills)
+template <bool SE3>
 __global__ void __launch_bounds__(ASM_THREADS)
 qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb, long long base, long long B) {
   extern __shared__ double smem[];
@@ -85,7 +88,7 @@ qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb,
     kin_forward(pg, s);
     kin_composite(pg, s);
     kin_standing(pg, s);
-    kin_se3pd(pg, io, inst, s);
+    if (SE3) kin_se3pd(pg, io, inst, s);
     kin_contacts(pg, s);
     const int n = pg->n, mg = pg->mg, nbx = pg->nbx;
     kin_assemble(pg, s, qb.P + inst * n * n, qb.qv + inst * n, qb.G + inst * mg * n, qb.lg + inst * mg,
@@ -372,7 +375,7 @@ static cudaError_t raise_dyn_smem(K kernel, int bytes, int (&mark)[64]) {
   return e;
 }
 static int g_mark_fd[64];
-static int g_mark_asm[64], g_mark_id[64], g_mark_admm128[64], g_mark_admm512[64], g_mark_kinwarp[64], g_mark_idsaved[64];
+static int g_mark_asm[64], g_mark_asm_se3[64], g_mark_id[64], g_mark_admm128[64], g_mark_admm512[64], g_mark_kinwarp[64], g_mark_idsaved[64];
 // ---- ADMM dispatch: register-resident kernel when the KKT matrix fits the register file, shared-memory kernel otherwise
 // returns a code TC * 100 + NB, or 0 for the shared-memory kernel
 static int reg_tile(int NK) {
@@ -573,7 +576,8 @@ static int configure_kernels(const DevProgram& p) {
   const int ksm = kin_smem_doubles(p.nb, p.nq, p.nv, p.ndes, p.ncontacts, p.N) * 8;
   const int asmem = admm_smem_doubles(p.n, p.mg, p.nbx) * 8;
   if (ksm > 227 * 1024) return qpc_fail(QPC_ERR_LIMIT, "mechanism does not fit the 227 KB shared memory of one CTA");
-  CUDA_TRY(raise_dyn_smem(qpc_assemble_kernel, ksm, g_mark_asm));
+  CUDA_TRY(raise_dyn_smem(qpc_assemble_kernel<false>, ksm, g_mark_asm));
+  CUDA_TRY(raise_dyn_smem(qpc_assemble_kernel<true>, ksm, g_mark_asm_se3));
   CUDA_TRY(raise_dyn_smem(qpc_inverse_dynamics_kernel, ksm, g_mark_id));
   if (kin_warp_per_instance(p, ksm)) {
     int dev = 0;
@@ -690,8 +694,9 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
     }
     if (timed) cudaEventRecord(c->be.ev[0], s);
     const bool kwarp = kin_warp_per_instance(p, ksm);
-    if (kwarp) CUDA_TRY(kin_warp_assemble(dp, io, qb, lo, hi, ksm, s));
-    else qpc_assemble_kernel<<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
+    if (kwarp) CUDA_TRY(kin_warp_assemble(dp, io, qb, lo, hi, ksm, s, p.nse3 > 0));
+    else if (p.nse3) qpc_assemble_kernel<true><<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
+    else qpc_assemble_kernel<false><<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
     if (timed) cudaEventRecord(c->be.ev[1], s);
     if (p.n > 0) {
       // Fast path with the diagonal-cost free variables eliminated: only for tolerances above the floor that form puts
@@ -1399,7 +1404,8 @@ int qpc_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
     qb.lb = lb;
     qb.ub = ub;
     if (desired_out) qb.des = desired_out;
-    qpc_assemble_kernel<<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qb, 0, B);
+    if (p.nse3) qpc_assemble_kernel<true><<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qb, 0, B);
+    else qpc_assemble_kernel<false><<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qb, 0, B);
     c->be.launches += 1;
     CUDA_TRY(cudaGetLastError());
     return QPC_OK;
@@ -1425,7 +1431,8 @@ int qpc_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
   }
   rc = stage_tick_parameters(c, B, in, true, true, io, s);
   if (rc) return rc;
-  qpc_assemble_kernel<<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qp_view(b), 0, B);
+  if (p.nse3) qpc_assemble_kernel<true><<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qp_view(b), 0, B);
+  else qpc_assemble_kernel<false><<<launch_grid(B), ASM_THREADS, ksm, s>>>(dp, io, qp_view(b), 0, B);
   c->be.launches += 1;
   CUDA_TRY(cudaGetLastError());
   const long long n = p.n, mg = p.mg, nbx = p.nbx;

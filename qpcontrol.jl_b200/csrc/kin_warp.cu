@@ -14,6 +14,7 @@
 
 namespace qpc {
 
+template <bool SE3>  // see qpc_assemble_kernel (api.cu)
 __global__ void __launch_bounds__(32 * KIN_WPC, KIN_WARP_MIN_CTAS)
 qpc_assemble_warp_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb, long long base, long long B) {
   extern __shared__ double smem_all[];
@@ -25,7 +26,7 @@ qpc_assemble_warp_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffer
     kin_forward(pg, s);
     kin_composite(pg, s);
     kin_standing(pg, s);
-    kin_se3pd(pg, io, inst, s);
+    if (SE3) kin_se3pd(pg, io, inst, s);
     kin_contacts(pg, s);
     const int n = pg->n, mg = pg->mg, nbx = pg->nbx;
     kin_assemble(pg, s, qb.P + inst * n * n, qb.qv + inst * n, qb.G + inst * mg * n, qb.lg + inst * mg,
@@ -92,15 +93,18 @@ static unsigned warp_grid(long long count) {
 }
 
 cudaError_t kin_warp_configure(int ksm_bytes) {
-  cudaError_t e = cudaFuncSetAttribute(qpc_assemble_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(qpc_assemble_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        KIN_WPC * ksm_bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(qpc_assemble_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KIN_WPC * ksm_bytes);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(qpc_inverse_dynamics_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               KIN_WPC * ksm_bytes);
 }
 cudaError_t kin_warp_assemble(const DevProgram* dp, const BatchIO& io, const QpBuffers& qb, long long lo, long long hi,
-                              int ksm_bytes, cudaStream_t s) {
-  qpc_assemble_warp_kernel<<<warp_grid(hi - lo), dim3(32, KIN_WPC), KIN_WPC * ksm_bytes, s>>>(dp, io, qb, lo, hi);
+                              int ksm_bytes, cudaStream_t s, bool se3) {
+  if (se3) qpc_assemble_warp_kernel<true><<<warp_grid(hi - lo), dim3(32, KIN_WPC), KIN_WPC * ksm_bytes, s>>>(dp, io, qb, lo, hi);
+  else qpc_assemble_warp_kernel<false><<<warp_grid(hi - lo), dim3(32, KIN_WPC), KIN_WPC * ksm_bytes, s>>>(dp, io, qb, lo, hi);
   return cudaGetLastError();
 }
 cudaError_t kin_warp_inverse_dynamics(const DevProgram* dp, const BatchIO& io, const QpBuffers& qb, double* tau,

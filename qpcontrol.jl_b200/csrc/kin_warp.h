@@ -29,7 +29,7 @@ cudaError_t kin_warp_id_saved(const DevProgram* dp, const QpBuffers& qb, double*
                               long long lo, long long hi, int bytes_per_instance, cudaStream_t s);
 cudaError_t kin_warp_configure(int ksm_bytes);
 cudaError_t kin_warp_assemble(const DevProgram* dp, const BatchIO& io, const QpBuffers& qb, long long lo, long long hi,
-                              int ksm_bytes, cudaStream_t s);
+                              int ksm_bytes, cudaStream_t s, bool se3);
 cudaError_t kin_warp_inverse_dynamics(const DevProgram* dp, const BatchIO& io, const QpBuffers& qb, double* tau,
                                       double* vdot, double* wrench, long long lo, long long hi, int ksm_bytes,
                                       cudaStream_t s);
