@@ -25,6 +25,11 @@ namespace qpc {
 #define QPC_MIN_SCALING 1e-4
 #define QPC_MAX_SCALING 1e4
 
+#if defined(QPC_THREAD_PER_INSTANCE)
+#define QPC_RED_DOUBLES 0      // no cross-thread reductions: one thread owns the QP
+#else
+#define QPC_RED_DOUBLES (32 * 16)
+#endif
 struct AdmmSmem {
   double *M;        // n x n   : P_bar -> S -> L -> L^-1 (lower) mirrored into the upper triangle
   double *Gs, *Gt;  // mg x n scaled G, n x mg its transpose
@@ -37,7 +42,7 @@ struct AdmmSmem {
 QPC_HD int admm_matrix_doubles(int n, int mg) { return n * n + 2 * mg * n; }
 QPC_HD int admm_vector_doubles(int n, int mg, int nbx) {
   const int m = mg + nbx;
-  return 7 * n + 9 * m + nbx + 32 * 16 + 32 + 8;
+  return 7 * n + 9 * m + nbx + QPC_RED_DOUBLES + 32 + 8;
 }
 QPC_HD int admm_smem_doubles(int n, int mg, int nbx) { return admm_matrix_doubles(n, mg) + admm_vector_doubles(n, mg, nbx); }
 // `mat` holds the three matrices (shared memory, or a per-CTA global scratch for QPs that do not fit), `b` the vectors
@@ -64,7 +69,7 @@ QPC_HD AdmmSmem admm_layout(double* mat, double* b, int n, int mg, int nbx) {
   s.dy = b;   b += m;
   s.ax = b;   b += m;
   s.cb = b;   b += nbx;
-  s.red = b;  b += 32 * 16;
+  s.red = b;  b += QPC_RED_DOUBLES;
   s.sc = b;   b += 32;
   return s;
 }
@@ -72,7 +77,7 @@ QPC_HD AdmmSmem admm_layout(double* mat, double* b, int n, int mg, int nbx) {
 // ---- block reductions of K values at once (K <= 16) ------------------------------------------------------------------
 template <int K, bool IS_MAX>
 QPC_DEV void block_reduce(double* v, double* red) {
-#if defined(__CUDA_ARCH__)
+#if !defined(QPC_SERIAL)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
   for (int k = 0; k < K; k++) {
@@ -100,7 +105,7 @@ QPC_DEV void block_reduce(double* v, double* red) {
 
 // sum of `acc` over the R adjacent lanes that share one output (R in {1,2,4,8}); every lane of the warp must call
 QPC_DEV double lane_group_sum(double acc, int R) {
-#if defined(__CUDA_ARCH__)
+#if !defined(QPC_SERIAL)
   for (int o = R >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
 #else
   (void)R;
@@ -108,7 +113,7 @@ QPC_DEV double lane_group_sum(double acc, int R) {
   return acc;
 }
 QPC_DEV int split_factor(int nout) {
-#if defined(__CUDA_ARCH__)
+#if !defined(QPC_SERIAL)
   int R = 1;
   while (R < 8 && nout * R * 2 <= (int)blockDim.x) R *= 2;
   return R;

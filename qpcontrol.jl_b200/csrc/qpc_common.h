@@ -13,12 +13,19 @@
 #define QPC_HD __host__ __device__ __forceinline__
 #define QPC_DEV __device__ __forceinline__
 #define QPC_DEVN __device__ __noinline__
+#if defined(QPC_THREAD_PER_INSTANCE)  // tiny_thread.cu: one THREAD per robot instance, workspace in local memory
+#define QPC_TID 0
+#define QPC_NT 1
+#define QPC_SYNC() ((void)0)
+#define QPC_SERIAL 1
+#else
 #define QPC_TID ((int)threadIdx.x)
 #define QPC_NT ((int)blockDim.x)
 #if defined(QPC_WARP_PER_INSTANCE)  // kin_warp.cu: blockDim = (32, instances per CTA), one warp per robot instance
 #define QPC_SYNC() __syncwarp()
 #else
 #define QPC_SYNC() __syncthreads()
+#endif
 #endif
 #define QPC_LDG(p) __ldg(p)
 #define QPC_UNROLL8 _Pragma("unroll 8")  // product loops: eight loads in flight instead of one dependent load per FMA
@@ -29,6 +36,7 @@
 #define QPC_TID 0
 #define QPC_NT 1
 #define QPC_SYNC() ((void)0)
+#define QPC_SERIAL 1
 #define QPC_LDG(p) (*(p))
 #define QPC_UNROLL8
 #endif

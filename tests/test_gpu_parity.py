@@ -116,27 +116,52 @@ def test_acrobot_point_task(orc):
     parity.assert_tick_parity(sub, ref, low.program)
 
 
-def test_warp_per_instance_kinematics_equal_the_cta_kernels(tmp_path):
-    """Tiny mechanisms run the kinematics kernels one warp per instance (kin_warp.cu); QPC_KIN_WARP=0 (read once per
-    process, hence the subprocess) forces the CTA-per-instance kernels.  Same code, same arithmetic: identical results,
-    also on an odd batch (the last CTA holds one instance and an idle warp)."""
+def _acrobot_in_subprocess(tmp_path, name, B, seed, **env):
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = str(tmp_path / "cta.npz")
+    out = str(tmp_path / name)
     script = ("import sys, numpy as np; sys.path.insert(0, %r); import qpc_loader; qpc_loader.load(); "
               "from qpcontrol_jl_b200 import scenarios; "
               "mech, low, task = scenarios.acrobot_point_task(); "
-              "q, v, des = scenarios.acrobot_random_inputs(mech, 1001, seed=12); r = low(q, v, des); "
-              "np.savez(%r, tau=r.tau, vdot=r.vdot, status=r.status, iters=r.iters)" % (root, out))
-    subprocess.run([sys.executable, "-c", script], check=True, env=dict(os.environ, QPC_KIN_WARP="0"), timeout=600)
-    cta = np.load(out)
+              "q, v, des = scenarios.acrobot_random_inputs(mech, %d, seed=%d); r = low(q, v, des); "
+              "np.savez(%r, tau=r.tau, vdot=r.vdot, status=r.status, iters=r.iters)" % (root, B, seed, out))
+    subprocess.run([sys.executable, "-c", script], check=True, env=dict(os.environ, **env), timeout=600)
+    return np.load(out)
+
+
+def test_warp_per_instance_kinematics_equal_the_cta_kernels(tmp_path):
+    """Tiny mechanisms on the three-kernel path (QPC_TINY_THREAD=0) run the kinematics kernels one warp per instance
+    (kin_warp.cu); QPC_KIN_WARP=0 (read once per process, hence the subprocesses) forces the CTA-per-instance kernels.
+    Same code, same arithmetic: identical results, also on an odd batch (the last CTA holds one instance and an idle
+    warp)."""
+    cta = _acrobot_in_subprocess(tmp_path, "cta.npz", 1001, 12, QPC_KIN_WARP="0", QPC_TINY_THREAD="0")
+    res = _acrobot_in_subprocess(tmp_path, "warp.npz", 1001, 12, QPC_TINY_THREAD="0")
+    assert np.array_equal(res["status"], cta["status"]) and np.array_equal(res["iters"], cta["iters"])
+    assert np.array_equal(res["tau"], cta["tau"]) and np.array_equal(res["vdot"], cta["vdot"])
+
+
+def test_thread_per_instance_tick_equals_the_three_kernel_path(tmp_path, orc):
+    """Tiny mechanisms run the WHOLE tick in one kernel, one thread per instance (tiny_thread.cu: kin.cuh + admm.cuh in the
+    QPC_THREAD_PER_INSTANCE execution model).  Against the three-kernel path (QPC_TINY_THREAD=0, subprocess; its solver is
+    the register-tile kernel, so iterates differ in rounding: same statuses, results to 1e-9) on an odd batch, and
+    against the oracle."""
+    three = _acrobot_in_subprocess(tmp_path, "three.npz", 4097, 13, QPC_TINY_THREAD="0")
     mech, low, task = scenarios.acrobot_point_task()
-    q, v, des = scenarios.acrobot_random_inputs(mech, 1001, seed=12)
+    q, v, des = scenarios.acrobot_random_inputs(mech, 4097, seed=13)
+    dev = low.finalize()
+    n0 = dev.launch_count()
     res = low(q, v, des)
-    assert np.array_equal(res.status, cta["status"]) and np.array_equal(res.iters, cta["iters"])
-    assert np.array_equal(res.tau, cta["tau"]) and np.array_equal(res.vdot, cta["vdot"])
+    assert dev.launch_count() - n0 <= 4  # one launch per chunk (three chunks on side streams), not three per chunk
+    assert np.array_equal(res.status, three["status"])
+    assert np.max(np.abs(res.iters - three["iters"])) <= 25  # one termination-check interval
+    scale = max(1.0, np.max(np.abs(three["tau"])))
+    assert np.max(np.abs(res.tau - three["tau"])) <= 1e-7 * scale
+    assert np.max(np.abs(res.vdot - three["vdot"])) <= 1e-7 * max(1.0, np.max(np.abs(three["vdot"])))
+    ref = orc.OracleController(low.program).solve_batch(q[:512], v[:512], desired=des[:512])
+    sub = type(res)(res.tau[:512], res.vdot[:512], res.wrenches[:512], res.status[:512], res.iters[:512], res.residuals[:512])
+    parity.assert_tick_parity(sub, ref, low.program)
 
 
 # (30,30), (68,71): register tiles; (40,110): shared-memory kernel, 128-thread CTAs; (60,100): shared-memory kernel,
