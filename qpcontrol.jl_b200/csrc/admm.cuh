@@ -34,7 +34,7 @@ struct AdmmSmem {
   double *M;        // n x n   : P_bar -> S -> L -> L^-1 (lower) mirrored into the upper triangle
   double *Gs, *Gt;  // mg x n scaled G, n x mg its transpose
   double *D, *qs, *x, *xt, *rhs, *tv, *dx;        // n
-  double *E, *l, *u, *z, *y, *rho, *w, *dy, *ax;  // m = mg + nbx
+  double *E, *l, *u, *z, *y, *rho, *w, *dy, *ax, *rinv;  // m = mg + nbx (rinv = 1 / rho: OSQP's rho_inv_vec)
   double *cb;                                     // nbx scaled box coefficient E_b D_j
   double *red;                                    // reduction scratch: 32 warps x 16
   double *sc;                                     // scalars
@@ -42,7 +42,7 @@ struct AdmmSmem {
 QPC_HD int admm_matrix_doubles(int n, int mg) { return n * n + 2 * mg * n; }
 QPC_HD int admm_vector_doubles(int n, int mg, int nbx) {
   const int m = mg + nbx;
-  return 7 * n + 9 * m + nbx + QPC_RED_DOUBLES + 32 + 8;
+  return 7 * n + 10 * m + nbx + QPC_RED_DOUBLES + 32 + 8;
 }
 QPC_HD int admm_smem_doubles(int n, int mg, int nbx) { return admm_matrix_doubles(n, mg) + admm_vector_doubles(n, mg, nbx); }
 // `mat` holds the three matrices (shared memory, or a per-CTA global scratch for QPs that do not fit), `b` the vectors
@@ -68,6 +68,7 @@ QPC_HD AdmmSmem admm_layout(double* mat, double* b, int n, int mg, int nbx) {
   s.w = b;    b += m;
   s.dy = b;   b += m;
   s.ax = b;   b += m;
+  s.rinv = b; b += m;
   s.cb = b;   b += nbx;
   s.red = b;  b += QPC_RED_DOUBLES;
   s.sc = b;   b += 32;
@@ -201,6 +202,7 @@ QPC_DEV void admm_set_rho(const AdmmSmem& s, int m, double rho) {
     else if (s.u[i] - s.l[i] < QPC_RHO_TOL) r = QPC_RHO_EQ_FACTOR * rho;
     else r = rho;
     s.rho[i] = r;
+    s.rinv[i] = 1.0 / r;
   }
   QPC_SYNC();
 }
@@ -273,8 +275,12 @@ QPC_DEV void admm_factor(const AdmmSmem& s, const double* __restrict__ P, int n,
 
 // The solver.  `smem` must hold admm_smem_doubles(n, mg, nbx) doubles, or only admm_vector_doubles when `gmat`
 // (admm_matrix_doubles of global scratch owned by this CTA) is given.
-QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg, int nbx, double* smem,
+// CN / CMG / CNBX >= 0 fix the dimensions at compile time (the thread-per-instance tick of tiny_thread.cu: every loop of a
+// 2 x 3 QP unrolls); -1 = the run-time arguments.
+template <int CN = -1, int CMG = -1, int CNBX = -1>
+QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n_, int mg_, int nbx_, double* smem,
                         double* gmat = nullptr) {
+  const int n = CN >= 0 ? CN : n_, mg = CMG >= 0 ? CMG : mg_, nbx = CNBX >= 0 ? CNBX : nbx_;
   const int tid = QPC_TID, nt = QPC_NT;
   const int m = mg + nbx, nx0 = n - nbx;
   AdmmSmem s = gmat ? admm_layout(gmat, smem, n, mg, nbx) : admm_layout(smem, smem + admm_matrix_doubles(n, mg), n, mg, nbx);
@@ -376,6 +382,7 @@ QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg
   double pri_res = 0, dua_res = 0;
   const double alpha = st.alpha;
   const int Rn = split_factor(n), Gn = nt / Rn, sn = tid % Rn;
+  int to_check = st.check_termination, to_adapt = st.adaptive_rho ? st.adaptive_rho_interval : 0;  // countdowns (no modulo)
   for (iter = 1; iter <= st.max_iter; iter++) {
     // rhs = sigma x - q + A'(rho z - y)
     admm_At_times(s, n, mg, nbx, s.w, s.rhs, st.sigma, s.x, s.qs);
@@ -414,7 +421,7 @@ QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg
     QPC_SYNC();
     for (int i = tid; i < m; i += nt) {
       const double zr = alpha * s.ax[i] + (1 - alpha) * s.z[i];
-      const double zn = fmin(fmax(zr + s.y[i] / s.rho[i], s.l[i]), s.u[i]);
+      const double zn = fmin(fmax(zr + s.y[i] * s.rinv[i], s.l[i]), s.u[i]);
       const double d = s.rho[i] * (zr - zn);
       s.dy[i] = d;
       s.y[i] += d;
@@ -422,8 +429,10 @@ QPC_DEV void admm_solve(const Settings& st, const AdmmProblem& pb, int n, int mg
       s.w[i] = s.rho[i] * zn - s.y[i];
     }
     QPC_SYNC();
-    const bool check = st.check_termination && (iter % st.check_termination == 0);
-    const bool adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
+    const bool check = st.check_termination && --to_check == 0;
+    const bool adapt = st.adaptive_rho && st.adaptive_rho_interval && --to_adapt == 0;
+    if (check) to_check = st.check_termination;
+    if (adapt) to_adapt = st.adaptive_rho_interval;
     if (!check && !adapt && iter != st.max_iter) continue;
     // ---- residuals --------------------------------------------------------------------------
     double* Px = s.xt;   // free between iterations

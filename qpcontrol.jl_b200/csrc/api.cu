@@ -592,7 +592,7 @@ static int configure_kernels(const DevProgram& p) {
   if (asmem <= ADMM_BIG_SMEM) CUDA_TRY(raise_dyn_smem(qpc_admm_kernel<ADMM_THREADS>, asmem, g_mark_admm128));
   if (const int tiny = tiny_thread_class(p); tiny >= 0) {
     std::lock_guard<std::mutex> lock(g_attr_mu);
-    CUDA_TRY(tiny_thread_configure(tiny));
+    CUDA_TRY(tiny_thread_configure(tiny, p));
   }
   {
     const int idsm = kin_id_smem_doubles(p.nb, p.nv, p.ndes, p.ncontacts, p.N) * 8;
@@ -704,7 +704,7 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
     const int tiny = tiny_on ? tiny_thread_class(p) : -1;
     if (tiny >= 0) {
       if (timed) cudaEventRecord(c->be.ev[1], s);
-      CUDA_TRY(tiny_thread_tick(tiny, dp, p.settings, io, qb, tau, vdot, wrench, lo, hi, s));
+      CUDA_TRY(tiny_thread_tick(tiny, p, dp, io, qb, tau, vdot, wrench, lo, hi, s));
       if (timed) {
         cudaEventRecord(c->be.ev[2], s);
         cudaEventRecord(c->be.ev[3], s);

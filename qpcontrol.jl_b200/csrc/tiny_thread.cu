@@ -17,8 +17,9 @@
 
 namespace qpc {
 
-template <int KWS, int AWS>
-__global__ void __launch_bounds__(TINY_THREADS)
+// CN / CMG / CNBX: the QP's dimensions at compile time (every solver loop unrolls), or -1 = read from the program
+template <int KWS, int AWS, int CN = -1, int CMG = -1, int CNBX = -1>
+__global__ void __launch_bounds__(TINY_THREADS, QPC_TINY_MINBLOCKS)
 qpc_tiny_tick_kernel(const DevProgram* __restrict__ pg, Settings st, BatchIO io, QpBuffers qb, double* tau, double* vdot,
                      double* wrench, long long base, long long B) {
   const long long inst = base + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -31,7 +32,7 @@ qpc_tiny_tick_kernel(const DevProgram* __restrict__ pg, Settings st, BatchIO io,
   kin_standing(pg, s);
   kin_se3pd(pg, io, inst, s);
   kin_contacts(pg, s);
-  const int n = pg->n, mg = pg->mg, nbx = pg->nbx;
+  const int n = CN >= 0 ? CN : pg->n, mg = CMG >= 0 ? CMG : pg->mg, nbx = CNBX >= 0 ? CNBX : pg->nbx;
   double* P = aws;
   double* qv = P + n * n;
   double* G = qv + n;
@@ -62,7 +63,7 @@ qpc_tiny_tick_kernel(const DevProgram* __restrict__ pg, Settings st, BatchIO io,
       pb.y0 = pb.y;
       pb.rho_io = qb.rho + inst;
     }
-    admm_solve(st, pb, n, mg, nbx, ws);
+    admm_solve<CN, CMG, CNBX>(st, pb, n, mg, nbx, ws);
   } else {
     qb.status[inst] = 1;
     if (qb.iters) qb.iters[inst] = 0;
@@ -82,12 +83,18 @@ int tiny_thread_class(const DevProgram& p) {
   return -1;
 }
 
+// kernel of a size class; the Acrobot demo's QP (2 variables, 3 equality rows, no box rows) has its own instantiation
+typedef void (*TinyKernel)(const DevProgram*, Settings, BatchIO, QpBuffers, double*, double*, double*, long long, long long);
+static TinyKernel tiny_kernel(int cls, const DevProgram& p) {
+  if (cls == 0 && p.n == 2 && p.mg == 3 && p.nbx == 0) return qpc_tiny_tick_kernel<TINY_KWS[0], TINY_AWS[0], 2, 3, 0>;
+  return cls == 0 ? qpc_tiny_tick_kernel<TINY_KWS[0], TINY_AWS[0]> : qpc_tiny_tick_kernel<TINY_KWS[1], TINY_AWS[1]>;
+}
+
 // The per-thread workspace is a local array: make sure the device's per-thread stack limit covers the kernel's frame
 // (set once at finalize, outside steady state -- changing the limit reallocates the device's local-memory pool).
-cudaError_t tiny_thread_configure(int cls) {
+cudaError_t tiny_thread_configure(int cls, const DevProgram& p) {
   cudaFuncAttributes fa;
-  cudaError_t e = cls == 0 ? cudaFuncGetAttributes(&fa, qpc_tiny_tick_kernel<TINY_KWS[0], TINY_AWS[0]>)
-                           : cudaFuncGetAttributes(&fa, qpc_tiny_tick_kernel<TINY_KWS[1], TINY_AWS[1]>);
+  cudaError_t e = cudaFuncGetAttributes(&fa, tiny_kernel(cls, p));
   if (e != cudaSuccess) return e;
   size_t cur = 0;
   e = cudaDeviceGetLimit(&cur, cudaLimitStackSize);
@@ -96,14 +103,11 @@ cudaError_t tiny_thread_configure(int cls) {
   return cur >= need ? cudaSuccess : cudaDeviceSetLimit(cudaLimitStackSize, need);
 }
 
-cudaError_t tiny_thread_tick(int cls, const DevProgram* dp, const Settings& st, const BatchIO& io, const QpBuffers& qb,
+cudaError_t tiny_thread_tick(int cls, const DevProgram& p, const DevProgram* dp, const BatchIO& io, const QpBuffers& qb,
                              double* tau, double* vdot, double* wrench, long long lo, long long hi, cudaStream_t s) {
   const long long g = (hi - lo + TINY_THREADS - 1) / TINY_THREADS;
   if (g <= 0) return cudaSuccess;
-  if (cls == 0)
-    qpc_tiny_tick_kernel<TINY_KWS[0], TINY_AWS[0]><<<(unsigned)g, TINY_THREADS, 0, s>>>(dp, st, io, qb, tau, vdot, wrench, lo, hi);
-  else
-    qpc_tiny_tick_kernel<TINY_KWS[1], TINY_AWS[1]><<<(unsigned)g, TINY_THREADS, 0, s>>>(dp, st, io, qb, tau, vdot, wrench, lo, hi);
+  tiny_kernel(cls, p)<<<(unsigned)g, TINY_THREADS, 0, s>>>(dp, p.settings, io, qb, tau, vdot, wrench, lo, hi);
   return cudaGetLastError();
 }
 
