@@ -44,9 +44,12 @@ struct Backend {
   bool warp_admm = true;      // qpc_set_admm_warp: allow the one-warp-per-QP kernel (admm_warp.cuh)
   // chunked tick: sub-batches go to side streams so that one chunk's assembly / inverse dynamics and the tail of its
   // ADMM kernel overlap the next chunk's ADMM kernel
-  static constexpr int NSIDE = 4;
-  cudaStream_t side[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[NSIDE] = {nullptr, nullptr, nullptr, nullptr};
+#ifndef QPC_NSIDE
+#define QPC_NSIDE 4
+#endif
+  static constexpr int NSIDE = QPC_NSIDE;
+  cudaStream_t side[NSIDE] = {};
+  cudaEvent_t fork = nullptr, join[NSIDE] = {};
 };
 
 #include "admm.cuh"
@@ -799,8 +802,15 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
     if (rc) return rc;
   } else {
     CUDA_TRY(cudaEventRecord(c->be.fork, stream));
+    // host buffers: the first chunk's H2D copies and the last chunk's D2H copies are the only ones no kernel hides, so
+    // those two chunks are smaller (15 % of the batch each with four chunks)
+    auto cut = [&](int k) -> long long {
+      if (!hx || nchunk != 4) return B * k / nchunk;
+      static const double frac[5] = {0.0, 0.15, 0.5, 0.85, 1.0};
+      return k == nchunk ? B : (long long)(B * frac[k]);
+    };
     for (int k = 0; k < nchunk; k++) {
-      const long long lo = B * k / nchunk, hi = B * (k + 1) / nchunk;
+      const long long lo = cut(k), hi = cut(k + 1);
       CUDA_TRY(cudaStreamWaitEvent(c->be.side[k], c->be.fork, 0));
       int rc = tick_range(lo, hi, c->be.side[k], false, k);
       if (rc) return rc;

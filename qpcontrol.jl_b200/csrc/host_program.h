@@ -143,6 +143,29 @@ inline std::string compile_program(const HostController& hc, DevProgram& p) {
       if (depth[b] == d) p.level_body[k++] = b;
   }
   p.level_ptr[maxd + 1] = k;
+  {  // ancestor chains (root first, the body itself last) and descendant lists (deepest first)
+    int ka = 0, kd = 0;
+    for (int b = 0; b < m.nb; b++) {
+      p.anc_ptr[b] = ka;
+      if (ka + depth[b] + 1 > QPC_MAXANC) return "kinematic tree too deep for the ancestor tables";
+      int chain[QPC_MAXB], len = 0;
+      for (int a = b; a >= 0; a = m.parent[a]) chain[len++] = a;
+      for (int i = len - 1; i >= 0; i--) p.anc_idx[ka++] = chain[i];
+      p.desc_ptr[b] = kd;
+      for (int d = maxd; d > depth[b]; d--)
+        for (int c = 0; c < m.nb; c++) {
+          if (depth[c] != d) continue;
+          bool below = false;
+          for (int a = m.parent[c]; a >= 0; a = m.parent[a]) below = below || a == b;
+          if (below) {
+            if (kd >= QPC_MAXANC) return "kinematic tree too deep for the descendant tables";
+            p.desc_idx[kd++] = c;
+          }
+        }
+    }
+    p.anc_ptr[m.nb] = ka;
+    p.desc_ptr[m.nb] = kd;
+  }
   k = 0;
   for (int b = 0; b < m.nb; b++) {
     p.child_ptr[b] = k;

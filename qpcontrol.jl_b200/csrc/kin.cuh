@@ -161,7 +161,9 @@ QPC_DEV void kin_load(const DevProgram* __restrict__ pg, const BatchIO& io, long
 // step -- 8 levels x ~400 dependent flops with 60 of the 64 threads waiting at the barrier (38 % of the kernel's stalls).
 QPC_DEV void kin_forward(const DevProgram* __restrict__ pg, KinSmem& s) {
   const int nb = pg->nb;
-  // phase 1 (all bodies): local transform X_tree * X_joint(q) into H
+  double* loc = s.scr;  // nb * 12 local transforms (scr is free until phase 5)
+  double* jtwp = s.IC;  // joint twists, 6 of every body's 10 slots (IC is free until kin_composite)
+  // phase 1 (all bodies): local transform X_tree * X_joint(q)
   for (int b = QPC_TID; b < nb; b += QPC_NT) {
     const int jt = pg->jtype[b];
     const double* qj = s.q + pg->qoff[b];
@@ -179,22 +181,19 @@ QPC_DEV void kin_forward(const DevProgram* __restrict__ pg, KinSmem& s) {
     Xf Xt;
     for (int i = 0; i < 9; i++) Xt.R[i] = pg->XR[9 * b + i];
     Xt.p = ld3(pg->Xp + 3 * b);
-    xf_store(s.H + 12 * b, xf_mul(Xt, Xj));
+    xf_store(loc + 12 * b, xf_mul(Xt, Xj));
   }
   QPC_SYNC();
-  // phase 2 (level by level): H_b = H_parent * local
-  for (int lvl = 0; lvl < pg->nlevels; lvl++) {
-    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
-      const int b = pg->level_body[k];
-      const int par = pg->parent[b];
-      if (par >= 0) xf_store(s.H + 12 * b, xf_mul(xf_load(s.H + 12 * par), xf_load(s.H + 12 * b)));
-    }
-    QPC_SYNC();
-  }
-  // phase 3 (all bodies): world-frame motion subspaces, joint twist (parked in TW), world inertia
+  // phase 2 (all bodies, NO barrier between tree levels): every body composes its own ancestor chain, root first -- the
+  // products of a level-by-level sweep in the same order, so the same bits -- then its world-frame motion subspaces, its
+  // joint twist and its world inertia.  A warp runs the chain loop once per level either way; what goes away is one CTA
+  // barrier per level (Atlas: 11 levels; barriers were 37 % of this kernel's stall samples, profiles/r2_asm_v2_*).
   for (int b = QPC_TID; b < nb; b += QPC_NT) {
+    const int a0 = pg->anc_ptr[b], a1 = pg->anc_ptr[b + 1];
+    Xf H = xf_load(loc + 12 * pg->anc_idx[a0]);
+    for (int k = a0 + 1; k < a1; k++) H = xf_mul(H, xf_load(loc + 12 * pg->anc_idx[k]));
+    xf_store(s.H + 12 * b, H);
     const int jt = pg->jtype[b];
-    const Xf H = xf_load(s.H + 12 * b);
     const V3 ax = ld3(pg->axis + 3 * b);
     const int o = pg->voff[b];
     S6 jtw = s6_zero();
@@ -216,48 +215,41 @@ QPC_DEV void kin_forward(const DevProgram* __restrict__ pg, KinSmem& s) {
         jtw = jtw + s.v[o + c] * Sa + s.v[o + 3 + c] * Sl;
       }
     }
-    st6(s.TW + 6 * b, jtw);
+    st6(jtwp + 10 * b, jtw);
     si_store(s.IW + 10 * b, si_transform(H, si_load(pg->inertia + 10 * b)));
   }
   QPC_SYNC();
-  // phase 4 (level by level): twist = parent's + joint twist, bias = parent's + twist x joint twist
-  for (int lvl = 0; lvl < pg->nlevels; lvl++) {
-    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
-      const int b = pg->level_body[k];
-      const int par = pg->parent[b];
-      const S6 jtw = ld6(s.TW + 6 * b);
-      const S6 tw = body_twist(s, par) + jtw;
-      st6(s.TW + 6 * b, tw);
-      st6(s.BI + 6 * b, body_bias(s, par) + cross_motion(tw, jtw));
-    }
-    QPC_SYNC();
-  }
-  // phase 5 (all bodies): per-body momentum and Newton-Euler bias terms (summed in kin_composite)
+  // phase 3 (all bodies): twist = sum of the chain's joint twists, bias = sum of (twist x joint twist) along the chain,
+  // root first; then the body's momentum and Newton-Euler bias terms (summed in kin_composite)
   for (int b = QPC_TID; b < nb; b += QPC_NT) {
+    S6 tw = s6_zero(), bi = s6_zero();
+    for (int k = pg->anc_ptr[b]; k < pg->anc_ptr[b + 1]; k++) {
+      const S6 jtw = ld6(jtwp + 10 * pg->anc_idx[k]);
+      tw = tw + jtw;
+      bi = bi + cross_motion(tw, jtw);
+    }
+    st6(s.TW + 6 * b, tw);
+    st6(s.BI + 6 * b, bi);
     const SI Iw = si_load(s.IW + 10 * b);
-    const S6 tw = ld6(s.TW + 6 * b);
     st6(s.scr + 12 * b, si_mul(Iw, tw));
-    st6(s.scr + 12 * b + 6, newton_euler(Iw, ld6(s.BI + 6 * b), tw));
+    st6(s.scr + 12 * b + 6, newton_euler(Iw, bi, tw));
   }
   QPC_SYNC();
 }
 
-// composite rigid-body inertias (children summed into parents, deepest level first), centre of mass, momentum,
-// momentum_rate_bias, gravity wrench, world-frame momentum matrix
+// composite rigid-body inertias (every body sums its own subtree, deepest descendants first: one pass, no barrier per
+// level), centre of mass, momentum, momentum_rate_bias, gravity wrench, world-frame momentum matrix
 QPC_DEV void kin_composite(const DevProgram* __restrict__ pg, KinSmem& s) {
-  for (int lvl = pg->nlevels - 1; lvl >= 0; lvl--) {
-    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
-      const int b = pg->level_body[k];
-      double acc[10];
-      for (int i = 0; i < 10; i++) acc[i] = s.IW[10 * b + i];
-      for (int c = pg->child_ptr[b]; c < pg->child_ptr[b + 1]; c++) {
-        const int ch = pg->child_idx[c];
-        for (int i = 0; i < 10; i++) acc[i] += s.IC[10 * ch + i];
-      }
-      for (int i = 0; i < 10; i++) s.IC[10 * b + i] = acc[i];
+  for (int b = QPC_TID; b < pg->nb; b += QPC_NT) {
+    double acc[10];
+    for (int i = 0; i < 10; i++) acc[i] = 0.0;
+    for (int k = pg->desc_ptr[b]; k < pg->desc_ptr[b + 1]; k++) {
+      const int d = pg->desc_idx[k];
+      for (int i = 0; i < 10; i++) acc[i] += s.IW[10 * d + i];
     }
-    QPC_SYNC();
+    for (int i = 0; i < 10; i++) s.IC[10 * b + i] = acc[i] + s.IW[10 * b + i];
   }
+  QPC_SYNC();
   // totals: 12 sums over bodies + centre of mass from the roots' composite inertia
   for (int c = QPC_TID; c < 12; c += QPC_NT) {
     double a = 0;

@@ -14,6 +14,7 @@
 #define QPC_MAXPATH 512 // total path entries over all tasks
 #define QPC_MAXDES 160  // total desired dimension
 #define QPC_MAXW 256    // matrix-weight storage (doubles)
+#define QPC_MAXANC 1200 // total entries of the per-body ancestor / descendant lists (sum of depths)
 #define QPC_MAXSE3 4    // SE3PDControllers evaluated on the device
 #define QPC_MAXSEG 6    // Interpolated pieces of one (Piecewise) trajectory
 
@@ -71,6 +72,10 @@ struct DevProgram {
   int vbody[QPC_MAXV];
   int nlevels, level_ptr[QPC_MAXB + 1], level_body[QPC_MAXB];  // bodies grouped by depth
   int child_ptr[QPC_MAXB + 1], child_idx[QPC_MAXB];
+  // chain-walk sweeps (kin_forward / kin_composite): ancestors of body b including b itself, root first; and its proper
+  // descendants, deepest level first -- each body folds its own chain, one barrier per sweep instead of one per tree level
+  int anc_ptr[QPC_MAXB + 1], anc_idx[QPC_MAXANC];
+  int desc_ptr[QPC_MAXB + 1], desc_idx[QPC_MAXANC];
   double axis[QPC_MAXB * 3], XR[QPC_MAXB * 9], Xp[QPC_MAXB * 3];
   double inertia[QPC_MAXB * 10];  // body-frame SI (see qpc_common.h)
   double gravity[3], total_mass;

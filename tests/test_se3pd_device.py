@@ -126,9 +126,12 @@ def test_device_se3pd_through_the_c_abi(kind):
     des = np.tile(low2.program.default_desired(), (B, 1))
     des[:, off2:off2 + 6] = want
     res2 = low2(q, v, desired=des, check=False)
-    ok = ((res.status == 1) | (res.status == 2)) & ((res2.status == 1) | (res2.status == 2))
+    acc, acc2 = (res.status == 1) | (res.status == 2), (res2.status == 1) | (res2.status == 2)
+    ok = acc & acc2
     assert ok.mean() > 0.95
-    assert np.array_equal(res.status, res2.status)
+    # the two desireds differ in rounding (1e-12): accept / reject must agree; OPTIMAL vs ALMOST_OPTIMAL at the iteration
+    # limit may flip for an instance that converges slowly
+    assert np.array_equal(acc, acc2)
     assert np.max(np.abs(res.tau[ok] - res2.tau[ok])) <= 1e-6 * max(1.0, np.max(np.abs(res2.tau[ok])))
 
 
