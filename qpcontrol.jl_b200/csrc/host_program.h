@@ -256,8 +256,16 @@ inline std::string compile_program(const HostController& hc, DevProgram& p) {
       }
       d.path_len = npath - d.path_ptr;
     }
+    for (int c = 0; c < QPC_MAXV; c++) p.tsign[ti][c] = 0;
+    for (int e = d.path_ptr; e < d.path_ptr + d.path_len; e++) {
+      const int b = p.path_body[e];
+      for (int c = m.voff[b]; c < m.voff[b] + m.nvj[b]; c++) p.tsign[ti][c] = (signed char)p.path_sign[e];
+    }
     for (int i = 0; i < t.dim; i++) p.def_desired[t.des_off + i] = t.desired.empty() ? 0.0 : t.desired[i];
   }
+  p.nfixv = 0;
+  for (int i = 0; i < m.nv; i++)
+    if (p.vcol[i] < 0) p.fixv[p.nfixv++] = i;
   p.balance_row0 = -1;
   if (hc.floating >= 0) {
     if (m.jtype[hc.floating] != 2) return "floating joint must be a quaternion floating joint";

@@ -413,13 +413,14 @@ QPC_DEV void kin_contacts(const DevProgram* __restrict__ pg, KinSmem& s) {
   QPC_SYNC();
 }
 
-// rows of task_error = J vd + b - desired for one task into s.Jt (dim x nv) and s.bt (dim)
-// (tasks.jl:31-44,73-84,112-123,153-171,185-189,230-236,258-262)
-QPC_DEV void kin_task_rows(const DevProgram* __restrict__ pg, KinSmem& s, const DevTask& t) {
-  const int nv = pg->nv;
-  for (int i = QPC_TID; i < 6 * nv; i += QPC_NT) s.Jt[i] = 0.0;
-  QPC_SYNC();
-  const int kind = t.kind;
+// rows of task_error = J vd + b - desired for one task into Jt (dim x nv) and bt (dim)
+// (tasks.jl:31-44,73-84,112-123,153-171,185-189,230-236,258-262).  One velocity COLUMN per thread (every entry of Jt is
+// written, zeros included: no clearing pass, and the six columns of a floating joint go to six threads); the bias by the
+// first thread past the columns.  No barrier inside: the caller separates producing and consuming a buffer.
+QPC_DEV void kin_task_rows(const DevProgram* __restrict__ pg, const KinSmem& s, int ti, double* Jt, double* bt) {
+  const DevTask& t = pg->tasks[ti];
+  const int nv = pg->nv, kind = t.kind, dim = t.dim;
+  const int bias_tid = QPC_NT > nv ? nv : 0;
   if (kind <= 3) {  // path tasks: geometric Jacobian in `frame` (point task: the base frame)
     const Xf Xinv = xf_inv(body_to_root(s, t.frame));
     V3 p = mk3(0, 0, 0);
@@ -428,22 +429,23 @@ QPC_DEV void kin_task_rows(const DevProgram* __restrict__ pg, KinSmem& s, const 
       p = rot(rel.R, ld3(t.point)) + rel.p;
     }
     const int r0 = kind == 2 ? 3 : 0;
-    for (int e = QPC_TID; e < t.path_len; e += QPC_NT) {
-      const int b = pg->path_body[t.path_ptr + e];
-      const double sgn = (double)pg->path_sign[t.path_ptr + e];
-      for (int c = pg->voff[b]; c < pg->voff[b] + pg->nvj[b]; c++) {
-        S6 col = sgn * xmotion(Xinv, ld6(s.SW + 6 * c));
-        if (kind == 3) {
-          V3 pj = cross(col.w, p) + col.v;  // point_jacobian!: J_lin + J_ang x p
-          s.Jt[0 * nv + c] = pj.x;
-          s.Jt[1 * nv + c] = pj.y;
-          s.Jt[2 * nv + c] = pj.z;
-        } else {
-          for (int r = 0; r < t.dim; r++) s.Jt[r * nv + c] = s6_get(col, r0 + r);
-        }
+    for (int c = QPC_TID; c < nv; c += QPC_NT) {
+      const int sg = pg->tsign[ti][c];
+      if (sg == 0) {
+        for (int r = 0; r < dim; r++) Jt[r * nv + c] = 0.0;
+        continue;
+      }
+      S6 col = (double)sg * xmotion(Xinv, ld6(s.SW + 6 * c));
+      if (kind == 3) {
+        V3 pj = cross(col.w, p) + col.v;  // point_jacobian!: J_lin + J_ang x p
+        Jt[0 * nv + c] = pj.x;
+        Jt[1 * nv + c] = pj.y;
+        Jt[2 * nv + c] = pj.z;
+      } else {
+        for (int r = 0; r < dim; r++) Jt[r * nv + c] = s6_get(col, r0 + r);
       }
     }
-    if (QPC_TID == 0) {
+    if (QPC_TID == bias_tid) {
       // transform(state, -bias(source) + bias(target), frame): X [ a + (-T_frame) x (T_target - T_source) ]
       S6 rel = body_twist(s, t.target) - body_twist(s, t.source);
       S6 a = body_bias(s, t.target) - body_bias(s, t.source);
@@ -453,16 +455,17 @@ QPC_DEV void kin_task_rows(const DevProgram* __restrict__ pg, KinSmem& s, const 
         S6 T = xmotion(Xinv, rel);
         V3 pd = cross(T.w, p) + T.v;
         V3 bb = cross(T.w, pd) + cross(jv.w, p) + jv.v;
-        st3(s.bt, bb);
+        st3(bt, bb);
       } else {
-        for (int r = 0; r < t.dim; r++) s.bt[r] = s6_get(jv, r0 + r);
+        for (int r = 0; r < dim; r++) bt[r] = s6_get(jv, r0 + r);
       }
     }
   } else if (kind == 4) {
-    for (int r = QPC_TID; r < t.dim; r += QPC_NT) {
-      s.Jt[r * nv + pg->voff[t.joint] + r] = 1.0;
-      s.bt[r] = 0.0;
-    }
+    const int o = pg->voff[t.joint];
+    for (int c = QPC_TID; c < nv; c += QPC_NT)
+      for (int r = 0; r < dim; r++) Jt[r * nv + c] = (c == o + r) ? 1.0 : 0.0;
+    if (QPC_TID == bias_tid)
+      for (int r = 0; r < dim; r++) bt[r] = 0.0;
   } else {  // momentum-rate tasks: force-transform of the world momentum matrix to the centroidal frame
     const V3 com = ld3(s.tot);
     const int r0 = kind == 6 ? 3 : 0;
@@ -470,15 +473,46 @@ QPC_DEV void kin_task_rows(const DevProgram* __restrict__ pg, KinSmem& s, const 
       V3 aw = mk3(s.A[0 * nv + c], s.A[1 * nv + c], s.A[2 * nv + c]);
       V3 al = mk3(s.A[3 * nv + c], s.A[4 * nv + c], s.A[5 * nv + c]);
       S6 col = mk6(aw - cross(com, al), al);
-      for (int r = 0; r < t.dim; r++) s.Jt[r * nv + c] = s6_get(col, r0 + r);
+      for (int r = 0; r < dim; r++) Jt[r * nv + c] = s6_get(col, r0 + r);
     }
-    if (QPC_TID == 0) {
+    if (QPC_TID == bias_tid) {
       S6 hb = ld6(s.tot + 9);
       S6 hc = mk6(hb.w - cross(com, hb.v), hb.v);
-      for (int r = 0; r < t.dim; r++) s.bt[r] = s6_get(hc, r0 + r);
+      for (int r = 0; r < dim; r++) bt[r] = s6_get(hc, r0 + r);
     }
   }
-  QPC_SYNC();
+}
+// one task's rows into the QP from a finished (Jt, bt) buffer: residual r = b - desired + J_fixed vd_fixed, bounds, the free
+// columns of G, slack columns and slack cost
+QPC_DEV void kin_task_emit(const DevProgram* __restrict__ pg, const KinSmem& s, int ti, const double* Jt, const double* bt,
+                           double* P, double* G, double* lg, double* ug) {
+  const DevTask& t = pg->tasks[ti];
+  const int n = pg->n, nv = pg->nv, dim = t.dim, t0 = QPC_TID, nt = QPC_NT;
+  // the residual rows go to the LAST threads (the first ones are still busy with the next task's columns)
+  for (int k = nt - 1 - t0; k < dim; k += nt) {
+    double a = bt[k] - s.des[t.des_off + k];
+    for (int j = 0; j < pg->nfixv; j++) {
+      const int i = pg->fixv[j];
+      a += Jt[k * nv + i] * s.des[pg->vfix_des[i]];
+    }
+    lg[t.row0 + k] = ug[t.row0 + k] = -a;
+  }
+  for (int k = t0; k < dim * nv; k += nt) {
+    const int row = k / nv, i = k % nv;
+    if (pg->vcol[i] >= 0) G[(t.row0 + row) * n + pg->vcol[i]] = Jt[k];
+  }
+  if (t.mode != 0) {
+    for (int k = t0; k < dim; k += nt) G[(t.row0 + k) * n + t.scol0 + k] = -1.0;
+    if (t.mode == 1) {
+      for (int k = t0; k < dim; k += nt) P[(t.scol0 + k) * n + t.scol0 + k] = 2.0 * s.tw[ti];
+    } else {  // e'We with a possibly unsymmetric W: the Hessian is W + W'
+      const double* W = s.wm + t.w_off;
+      for (int k = t0; k < dim * dim; k += nt) {
+        const int a = k / dim, b = k % dim;
+        P[(t.scol0 + a) * n + t.scol0 + b] = W[a * dim + b] + W[b * dim + a];
+      }
+    }
+  }
 }
 
 // ---- QP assembly -------------------------------------------------------------------------------------------------------
@@ -512,35 +546,35 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
     ub[k] = s.cm[c] * s.ct[c * kin_ct_stride(N) + 12 + 3 * N + N * N];
   }
   QPC_SYNC();
-  for (int ti = 0; ti < pg->ntasks; ti++) {
-    const DevTask& t = pg->tasks[ti];
-    if (t.eliminated) continue;
-    kin_task_rows(pg, s, t);
-    double* r = s.bt + 8;
-    for (int k = t0; k < t.dim; k += nt) {
-      double a = s.bt[k] - s.des[t.des_off + k];
-      for (int i = 0; i < nv; i++)
-        if (pg->vcol[i] < 0) a += s.Jt[k * nv + i] * s.des[pg->vfix_des[i]];
-      r[k] = a;
-    }
-    QPC_SYNC();
-    for (int k = t0; k < t.dim * nv; k += nt) {
-      const int row = k / nv, i = k % nv;
-      if (pg->vcol[i] >= 0) G[(t.row0 + row) * n + pg->vcol[i]] = s.Jt[k];
-    }
-    for (int k = t0; k < t.dim; k += nt) lg[t.row0 + k] = ug[t.row0 + k] = -r[k];
-    if (t.mode != 0) {
-      for (int k = t0; k < t.dim; k += nt) G[(t.row0 + k) * n + t.scol0 + k] = -1.0;
-      if (t.mode == 1) {
-        for (int k = t0; k < t.dim; k += nt) P[(t.scol0 + k) * n + t.scol0 + k] = 2.0 * s.tw[ti];
-      } else {  // e'We with a possibly unsymmetric W: the Hessian is W + W'
-        const double* W = s.wm + t.w_off;
-        for (int k = t0; k < t.dim * t.dim; k += nt) {
-          const int a = k / t.dim, b = k % t.dim;
-          P[(t.scol0 + a) * n + t.scol0 + b] = W[a * t.dim + b] + W[b * t.dim + a];
-        }
+  // Task rows, software-pipelined over two (Jt, bt) buffers: in one barrier interval the threads produce task j's rows
+  // (one column each) and emit task j-1's into the QP -- one barrier per task instead of four (the per-task loop was 25 %
+  // of this kernel: profiles/r2_asm_v2_stalls_by_line.txt).  The second buffer is the dead per-body scratch when it is
+  // large enough, otherwise both steps use s.Jt with a barrier in between.
+  {
+    const bool two = 12 * pg->nb >= 6 * nv;
+    double *jc = s.Jt, *jp = s.scr, *bc = s.bt, *bp = s.bt + 8;  // buffer being produced / being emitted
+    int prev = -1;
+    for (int ti = 0; ti < pg->ntasks; ti++) {
+      if (pg->tasks[ti].eliminated) continue;
+      if (!two) {
+        kin_task_rows(pg, s, ti, jc, bc);
+        QPC_SYNC();
+        kin_task_emit(pg, s, ti, jc, bc, P, G, lg, ug);
+        QPC_SYNC();
+        continue;
       }
+      kin_task_rows(pg, s, ti, jc, bc);
+      if (prev >= 0) kin_task_emit(pg, s, prev, jp, bp, P, G, lg, ug);
+      QPC_SYNC();
+      prev = ti;
+      double* tj = jc;
+      jc = jp;
+      jp = tj;
+      double* tb = bc;
+      bc = bp;
+      bp = tb;
     }
+    if (prev >= 0) kin_task_emit(pg, s, prev, jp, bp, P, G, lg, ug);
     QPC_SYNC();
   }
   if (pg->floating >= 0) {  // add_wrench_balance_constraint! (momentum.jl:162-193)

@@ -92,6 +92,10 @@ struct DevProgram {
   double reg[QPC_MAXV];
   DevTask tasks[QPC_MAXT];
   int path_body[QPC_MAXPATH], path_sign[QPC_MAXPATH];
+  // column-parallel task rows (kin_task_rows): sign of velocity column c in path task t's Jacobian (0: its body is not on
+  // the path), and the velocities fixed by hard JointAccelerationTasks, ascending
+  signed char tsign[QPC_MAXT][QPC_MAXV];
+  int nfixv, fixv[QPC_MAXV];
   double Wbuf[QPC_MAXW];
   int nwmat;  // doubles of Wbuf in use (sum of dim^2 over the matrix-weighted tasks)
   DevContact contacts[QPC_MAXC];
