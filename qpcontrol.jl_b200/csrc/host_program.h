@@ -266,6 +266,9 @@ inline std::string compile_program(const HostController& hc, DevProgram& p) {
   p.nfixv = 0;
   for (int i = 0; i < m.nv; i++)
     if (p.vcol[i] < 0) p.fixv[p.nfixv++] = i;
+  p.nactive = 0;
+  for (int ti = 0; ti < p.ntasks; ti++)
+    if (!p.tasks[ti].eliminated) p.active[p.nactive++] = ti;
   p.balance_row0 = -1;
   if (hc.floating >= 0) {
     if (m.jtype[hc.floating] != 2) return "floating joint must be a quaternion floating joint";

@@ -554,8 +554,8 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
     const bool two = 12 * pg->nb >= 6 * nv;
     double *jc = s.Jt, *jp = s.scr, *bc = s.bt, *bp = s.bt + 8;  // buffer being produced / being emitted
     int prev = -1;
-    for (int ti = 0; ti < pg->ntasks; ti++) {
-      if (pg->tasks[ti].eliminated) continue;
+    for (int ia = 0; ia < pg->nactive; ia++) {
+      const int ti = pg->active[ia];
       if (!two) {
         kin_task_rows(pg, s, ti, jc, bc);
         QPC_SYNC();

@@ -96,6 +96,7 @@ struct DevProgram {
   // the path), and the velocities fixed by hard JointAccelerationTasks, ascending
   signed char tsign[QPC_MAXT][QPC_MAXV];
   int nfixv, fixv[QPC_MAXV];
+  int nactive, active[QPC_MAXT];  // tasks that own rows (not eliminated), addtask! order
   double Wbuf[QPC_MAXW];
   int nwmat;  // doubles of Wbuf in use (sum of dim^2 over the matrix-weighted tasks)
   DevContact contacts[QPC_MAXC];
