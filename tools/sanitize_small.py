@@ -25,3 +25,11 @@ for n, m in ((30, 30), (68, 71), (2, 3), (40, 110), (60, 100), (100, 100)):
 mech2, low2, task = scenarios.acrobot_point_task(OSQPSettings(max_iter=60))
 qa, va, da = scenarios.acrobot_random_inputs(mech2, 8, seed=2)
 print("acrobot", low2(qa, va, da, check=False).status)
+# round 2: the plant kernel, a program with a device-side SE3PDController (its own assembly instantiation), matrix weights
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+qp, vp, rp = low.simulate_plant(q[:2], v[:2], 2e-3, 1, ground_z=-10.0, substeps=2, check=False)
+print("plant", rp.status)
+import test_se3pd_device as T3
+mech3, low3, ctrl3, qnom3, se3, off3 = T3.make("piecewise", True, OSQPSettings(eps_abs=1e-5, eps_rel=1e-5, max_iter=60))
+q3, v3 = scenarios.atlas_random_states(mech3, qnom3, 3, seed=4)
+print("se3pd", low3(q3, v3, time=np.array([0.1, 0.7, 1.9]), check=False).status)
