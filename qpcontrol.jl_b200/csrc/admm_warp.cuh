@@ -48,6 +48,12 @@ struct WarpParams {
 
 #if defined(__CUDACC__)
 #define QPC_NOINLINE __noinline__
+#ifndef QPC_WARP_CPASYNC
+#define QPC_WARP_CPASYNC 1
+#endif
+#ifndef QPC_WARP_PBATCH
+#define QPC_WARP_PBATCH 4
+#endif
 #else
 #define QPC_NOINLINE
 #endif
@@ -148,8 +154,12 @@ struct WarpSolver {
     // scaled in place: lane k keeps its stored row and the pending factor s = 1 / pivot (applied once at the end); for
     // every other row the update in stored units is the same formula whether or not the row has been a pivot row
     // already, so the step is branch-free.
+    // The reciprocal of the NEXT pivot is taken right after the first FMA of a step (register 0 of lane k + 1 is then
+    // its diagonal entry) and travels with the pivot row: the ~60-cycle rcp chain overlaps the step's other 31 FMAs
+    // instead of sitting between the broadcast and the multiplier of every step.
     double s = 1.0;
     bool ok = true;
+    double dk_mine = rcp_pos(t[0]);
 #pragma unroll 1
     for (int k = 0; k < 32; k++) {
       double* rb = vb + (k & 1) * 34;
@@ -157,15 +167,17 @@ struct WarpSolver {
         double2* r2 = reinterpret_cast<double2*>(rb);
 #pragma unroll
         for (int c = 0; c < 16; c++) r2[c] = make_double2(t[2 * c], t[2 * c + 1]);
+        rb[32] = dk_mine;
       }
       __syncwarp();
       const double2* r2 = reinterpret_cast<const double2*>(rb);
       const double2 p0 = r2[0];
       const double piv = p0.x;
       ok = ok && (piv > 0.0);
-      const double dk = rcp_pos(piv);
+      const double dk = rb[32];
       const double m = (lane == k) ? 0.0 : t[0] * dk;
       t[0] = fma(-m, p0.y, t[1]);
+      dk_mine = rcp_pos(t[0]);
 #pragma unroll
       for (int c = 1; c < 16; c++) {
         const double2 p = r2[c];
@@ -283,9 +295,22 @@ struct WarpSolver {
     {
       double* Gs = sm + OFF_H;  // [MG][n] then b [MG]; needs MG (n + 1) <= 1024 + 32 NA doubles
       const int tot = MG * n;
+#if defined(__CUDA_ARCH__) && QPC_WARP_CPASYNC
+      // asynchronous 8-byte copies global -> shared: all ~40 per lane in flight at once (the register-staged loop paid one
+      // DRAM round trip per four elements: 7 % of the kernel's stall samples sat in this prologue)
 #pragma unroll 4
+      for (int idx = lane; idx < tot; idx += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(Gs + idx)),
+                     "l"(pb.G + idx));
+      if (lane < MG)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(Gs + tot + lane)),
+                     "l"(pb.lg + lane));
+      asm volatile("cp.async.commit_group;");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#else
       for (int idx = lane; idx < tot; idx += 32) Gs[idx] = pb.G[idx];
       if (lane < MG) Gs[tot + lane] = pb.lg[lane];
+#endif
       __syncwarp();
       const double* pa = lane < NA ? Gs + lane : Gs + tot;
       const int sa_ = lane < NA ? n : 1;
@@ -321,9 +346,17 @@ struct WarpSolver {
     for (int k = 0; k < NA; k++) {
       double* rb = vb + (k & 1) * 34;
       if (lane == k) {
-        double nrm2 = 0.0;
+        double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;  // four chains: this lane's serial section is every lane's wait
 #pragma unroll
-        for (int r = 0; r < MG; r++) nrm2 = fma(ca[r], ca[r], nrm2);
+        for (int r = 0; r + 3 < MG; r += 4) {
+          n0 = fma(ca[r], ca[r], n0);
+          n1 = fma(ca[r + 1], ca[r + 1], n1);
+          n2 = fma(ca[r + 2], ca[r + 2], n2);
+          n3 = fma(ca[r + 3], ca[r + 3], n3);
+        }
+#pragma unroll
+        for (int r = MG & ~3; r < MG; r++) n0 = fma(ca[r], ca[r], n0);
+        const double nrm2 = (n0 + n1) + (n2 + n3);
         const double nrm = sqrt(nrm2);
         const double alpha = ca[0] > 0.0 ? -nrm : nrm;
         const double den = nrm2 - alpha * ca[0];  // = v'v / 2 with v = x - alpha e_0
@@ -334,15 +367,21 @@ struct WarpSolver {
       }
       __syncwarp();
       const double beta = rb[MG];
-      double sa = 0.0, sb = 0.0;
+      double sa = 0.0, sb = 0.0, sa1 = 0.0, sb1 = 0.0;  // two chains per dot product
 #pragma unroll
-      for (int r = 0; r < MG; r++) {
-        const double vr = rb[r];
-        sa = fma(vr, ca[r], sa);
-        sb = fma(vr, cb[r], sb);
+      for (int r = 0; r + 1 < MG; r += 2) {
+        const double v0 = rb[r], v1 = rb[r + 1];
+        sa = fma(v0, ca[r], sa);
+        sb = fma(v0, cb[r], sb);
+        sa1 = fma(v1, ca[r + 1], sa1);
+        sb1 = fma(v1, cb[r + 1], sb1);
       }
-      sa *= beta;
-      sb *= beta;
+      if (MG & 1) {
+        sa = fma(rb[MG - 1], ca[MG - 1], sa);
+        sb = fma(rb[MG - 1], cb[MG - 1], sb);
+      }
+      sa = (sa + sa1) * beta;
+      sb = (sb + sb1) * beta;
       {
         const double v0 = rb[0];
         if (lane <= NA) RA[k * NAP + lane] = fma(-sa, v0, ca[0]);
@@ -528,10 +567,14 @@ struct WarpSolver {
     // column i of every lane's row
     {
       const double* pp = pb.P + (size_t)na * n + na + lane;
-#pragma unroll 4
-      for (int i = 0; i < 32; i++) {
-        const double pv = (hasb && i < nbx) ? pp[(size_t)i * n] : ((i == lane && !hasb) ? 1.0 : 0.0);
-        Hs[i * 32 + lane] += pv;
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += QPC_WARP_PBATCH) {  // QPC_WARP_PBATCH loads in flight before the first use
+        double pv[QPC_WARP_PBATCH];
+#pragma unroll
+        for (int i = 0; i < QPC_WARP_PBATCH; i++)
+          pv[i] = (hasb && i0 + i < nbx) ? pp[(size_t)(i0 + i) * n] : ((i0 + i == lane && !hasb) ? 1.0 : 0.0);
+#pragma unroll
+        for (int i = 0; i < QPC_WARP_PBATCH; i++) Hs[(i0 + i) * 32 + lane] += pv[i];
       }
     }
     const double tr = hasb ? Hs[lane * 32 + lane] : 0.0;

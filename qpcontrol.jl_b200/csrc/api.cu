@@ -544,7 +544,10 @@ static bool paa_is_diagonal(const DevProgram& p) {
 template <int MG, int NA>
 static cudaError_t launch_warp_t(const Settings& st, const QpBuffers& qb, int n, int nbx, long long base, long long B,
                                  int paa_diag, int* fb_list, int* fb_count, double* dbg, cudaStream_t stream) {
-  const int bytes = WarpSolver<MG, NA>::SMEM_DOUBLES * 8;
+  // QPC_WARP_PAD_SMEM=<bytes>: development knob, pads the dynamic shared memory to lower the resident CTAs per SM
+  // (occupancy scan: DESIGN.md 2.4)
+  static const int pad = [] { const char* e = getenv("QPC_WARP_PAD_SMEM"); return e ? atoi(e) : 0; }();
+  const int bytes = WarpSolver<MG, NA>::SMEM_DOUBLES * 8 + pad;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
