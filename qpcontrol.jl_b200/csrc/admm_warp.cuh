@@ -48,14 +48,14 @@ struct WarpParams {
 
 #if defined(__CUDACC__)
 #define QPC_NOINLINE __noinline__
-#ifndef QPC_WARP_CPASYNC
-#define QPC_WARP_CPASYNC 1
-#endif
-#ifndef QPC_WARP_PBATCH
-#define QPC_WARP_PBATCH 4
-#endif
 #else
 #define QPC_NOINLINE
+#endif
+#ifndef QPC_WARP_CPASYNC
+#define QPC_WARP_CPASYNC 1  // prologue: cp.async copies of G into shared memory (0: register-staged loop)
+#endif
+#ifndef QPC_WARP_PBATCH
+#define QPC_WARP_PBATCH 4   // rows of P_bb in flight before the first use
 #endif
 
 #if defined(__CUDACC__) || defined(QPC_WARP_EMU)  // QPC_WARP_EMU: tests/emu/warp_emu.cpp runs the body on CPU fibres
