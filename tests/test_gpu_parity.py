@@ -395,3 +395,35 @@ def test_warp_kernel_bench_settings_accuracy(orc):
     ok = (res.status == 1) & (truth["status"] == 1)
     err = parity.rel_err(res.tau[ok], truth["tau"][ok])
     assert np.median(err) < 5e-5 and np.percentile(err, 99) < 3e-3 and err.max() < 2e-2
+
+
+@pytest.mark.parametrize("variant", ["weighted", "contact"])
+def test_thread_per_instance_tick_generic_dimensions(orc, variant):
+    """The thread-per-instance tick's GENERIC instantiations (run-time QP dimensions; the Acrobot demo's 2 x 3 QP has its
+    own): the arm with a WEIGHTED point task (slack variables: 5 x 3) and with a contact point on the tip next to a weighted
+    joint task (box rows, wrench output) -- against the oracle, one launch per chunk."""
+    from qpcontrol_jl_b200 import MomentumBasedController, PointAccelerationTask, JointAccelerationTask
+    from qpcontrol_jl_b200.mechanism import acrobot
+    mech = acrobot()
+    low = MomentumBasedController(mech, OSQPSettings.test_suite(), N=4)
+    tip = mech.nb - 1
+    if variant == "weighted":
+        low.addtask(PointAccelerationTask(mech, -1, tip, scenarios.ACROBOT_POINT), 3.0)
+    else:
+        c = low.addcontact(tip, scenarios.ACROBOT_POINT, (0.0, 0.0, 1.0), 0.7)
+        c.maxnormalforce, c.weight = 50.0, 1e-3
+        for j in range(mech.nb):
+            if len(mech.velocity_range(j)):
+                low.addtask(JointAccelerationTask(mech, j), 2.0)
+    for j in range(mech.nb):
+        low.regularize(j, 1e-3)
+    B = 777
+    q, v, des = scenarios.acrobot_random_inputs(mech, B, seed=21)
+    desired = np.zeros((B, low.program.ndes))
+    desired[:, :min(3, low.program.ndes)] = des[:, :min(3, low.program.ndes)]
+    dev = low.finalize()
+    n0 = dev.launch_count()
+    res = low(q, v, desired, check=False)
+    assert dev.launch_count() - n0 == 1  # below 4096 instances: one chunk, ONE kernel for the whole tick
+    ref = orc.OracleController(low.program).solve_batch(q, v, desired=desired)
+    parity.assert_tick_parity(res, ref, low.program)
