@@ -97,8 +97,19 @@ QPC_DEV void kin_save(const DevProgram* __restrict__ pg, const KinSmem& s, doubl
 QPC_DEV void kin_id_load(const DevProgram* __restrict__ pg, KinSmem& s, const double* __restrict__ src,
                          const double* __restrict__ des) {
   const int tot = kin_save_doubles(pg->nb, pg->nv, pg->ncontacts, pg->N);
+#if defined(__CUDA_ARCH__) && !defined(QPC_THREAD_PER_INSTANCE)
+  // asynchronous copies global -> shared: every element of the 8.7 KB block in flight at once (a register-staged loop pays
+  // one DRAM round trip per unrolled group, and this epilogue is all latency)
+  for (int i = QPC_TID; i < tot; i += QPC_NT)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(s.SW + i)), "l"(src + i));
+  for (int i = QPC_TID; i < pg->ndes; i += QPC_NT)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(s.des + i)), "l"(des + i));
+  asm volatile("cp.async.commit_group;");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#else
   for (int i = QPC_TID; i < tot; i += QPC_NT) s.SW[i] = src[i];
   for (int i = QPC_TID; i < pg->ndes; i += QPC_NT) s.des[i] = des[i];
+#endif
   QPC_SYNC();
 }
 
@@ -611,32 +622,27 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
 QPC_DEV void kin_rnea(const DevProgram* __restrict__ pg, KinSmem& s, const double* vd, double* ext, double* acc,
                       double* tau_out, bool zero_floating) {
   const int nv = pg->nv, nb = pg->nb;
-  // forward: spatial accelerations with gravity as root acceleration, joint wrench = I a + T x* I T - ext
-  for (int lvl = 0; lvl < pg->nlevels; lvl++) {
-    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
-      const int b = pg->level_body[k], par = pg->parent[b];
-      S6 a = par < 0 ? mk6(mk3(0, 0, 0), -ld3(pg->gravity)) : ld6(acc + 6 * par);
-      for (int c = pg->voff[b]; c < pg->voff[b] + pg->nvj[b]; c++) a = a + vd[c] * ld6(s.SW + 6 * c);
-      a = a + (body_bias(s, b) - body_bias(s, par));
-      st6(acc + 6 * b, a);
-    }
-    QPC_SYNC();
-  }
+  // forward, as a chain walk (no barrier per tree level): with gravity as the root acceleration,
+  //   a_b = a_root + bias_b + sum over the ancestor chain of vd_c S_c
+  // (the bias differences of a level-by-level sweep telescope), then the body's own wrench  I a + T x* I T - ext  into `acc`
+  const S6 a0 = mk6(mk3(0, 0, 0), -ld3(pg->gravity));
   for (int b = QPC_TID; b < nb; b += QPC_NT) {
-    S6 w = newton_euler(si_load(s.IW + 10 * b), ld6(acc + 6 * b), ld6(s.TW + 6 * b)) - ld6(ext + 6 * b);
-    st6(ext + 6 * b, w);
+    S6 a = a0;
+    for (int k = pg->anc_ptr[b]; k < pg->anc_ptr[b + 1]; k++) {
+      const int ab = pg->anc_idx[k];
+      for (int c = pg->voff[ab]; c < pg->voff[ab] + pg->nvj[ab]; c++) a = a + vd[c] * ld6(s.SW + 6 * c);
+    }
+    a = a + body_bias(s, b);
+    st6(acc + 6 * b, newton_euler(si_load(s.IW + 10 * b), a, ld6(s.TW + 6 * b)) - ld6(ext + 6 * b));
   }
   QPC_SYNC();
-  // backward: parents accumulate their children's wrenches, deepest level first
-  for (int lvl = pg->nlevels - 2; lvl >= 0; lvl--) {
-    for (int k = pg->level_ptr[lvl] + QPC_TID; k < pg->level_ptr[lvl + 1]; k += QPC_NT) {
-      const int b = pg->level_body[k];
-      S6 w = ld6(ext + 6 * b);
-      for (int c = pg->child_ptr[b]; c < pg->child_ptr[b + 1]; c++) w = w + ld6(ext + 6 * pg->child_idx[c]);
-      st6(ext + 6 * b, w);
-    }
-    QPC_SYNC();
+  // backward: the joint wrench of body b is the sum of the own wrenches over its subtree (deepest descendants first)
+  for (int b = QPC_TID; b < nb; b += QPC_NT) {
+    S6 w = s6_zero();
+    for (int k = pg->desc_ptr[b]; k < pg->desc_ptr[b + 1]; k++) w = w + ld6(acc + 6 * pg->desc_idx[k]);
+    st6(ext + 6 * b, w + ld6(acc + 6 * b));
   }
+  QPC_SYNC();
   for (int c = QPC_TID; c < nv; c += QPC_NT) {
     const int b = pg->vbody[c];
     double tau = dot(ld6(s.SW + 6 * c), ld6(ext + 6 * b));
