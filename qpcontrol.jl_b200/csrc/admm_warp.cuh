@@ -85,8 +85,11 @@ struct WarpSolver {
   static_assert(NA < 32 && NA <= MG && MG <= 32, "x_a columns plus the right-hand side must fit one column per lane");
   static constexpr int ME = MG - NA;
   static constexpr int MEP = ME > 0 ? ME : 1;
+  static constexpr int QR_NAP = NA + 1 + ((NA + 1) & 1);  // row stride of the QR scratch (even, >= NA + 1)
+  // the H area also holds the QR scratch before H exists: two [NA][QR_NAP] blocks (NA > 22: larger than H itself)
+  static constexpr int HAREA = 2 * NA * QR_NAP > 1024 ? 2 * NA * QR_NAP : 1024;
   static constexpr int OFF_H = 0;                     // H, element (i, lane) at i * 32 + lane; setup scratch before
-  static constexpr int OFF_W = OFF_H + 1024;          // W skewed: (k, j) at k * 32 + ((j + k) & 31)
+  static constexpr int OFF_W = OFF_H + HAREA;         // W skewed: (k, j) at k * 32 + ((j + k) & 31)
   static constexpr int OFF_A3 = OFF_W + NA * 32;      // A3 (a, j) at a * 32 + j
   static constexpr int OFF_U = OFF_A3 + MEP * 32;     // U = A3 K^-1, same layout
   static constexpr int OFF_V = OFF_U + MEP * 32;      // 2 x 34: iteration vectors / broadcast rows (+ one scalar each)
@@ -293,7 +296,7 @@ struct WarpSolver {
     double ca[MG], cb[MG];  // column `lane` of [G_a | b] (b in lane NA) and of G_b
     const bool hasb = lane < nbx;
     {
-      double* Gs = sm + OFF_H;  // [MG][n] then b [MG]; needs MG (n + 1) <= 1024 + 32 NA doubles
+      double* Gs = sm + OFF_H;  // [MG][n] then b [MG]; MG (n + 1) <= HAREA + 32 NA doubles (checked below)
       const int tot = MG * n;
 #if defined(__CUDA_ARCH__) && QPC_WARP_CPASYNC
       // asynchronous 8-byte copies global -> shared: all ~40 per lane in flight at once (the register-staged loop paid one
@@ -337,11 +340,13 @@ struct WarpSolver {
     // [G_a | b], RB: columns of G_b) and a zero enters at register MG - 1.  Retired positions therefore hold zeros in
     // every column, including the owner's, so the reflector needs no length bookkeeping: v = column - alpha e_0 over all
     // MG registers.  After NA steps registers 0 .. ME-1 hold the rows that became A3 / b3.
-    constexpr int NAP = NA + 1 + ((NA + 1) & 1);  // row stride of RA and RS (even, >= NA + 1)
+    constexpr int NAP = QR_NAP;                   // row stride of RA and RS (even, >= NA + 1)
     double* RA = sm + OFF_H;                       // [NA][NAP]: R (upper triangle) and Q1'b in column NA
     double* RB = RA + NA * NAP;                    // [NA][32]:  Q1'G_b
     double* RS = RB + NA * 32;                     // [NA][NAP]: R in the order the back-substitution consumes it
-    static_assert(NA * NAP * 2 + NA * 32 <= 1024 + NA * 32, "QR scratch must fit the H and W areas");
+    static_assert(NA * NAP * 2 + NA * 32 <= HAREA + NA * 32, "QR scratch must fit the H and W areas");
+    static_assert(MG <= 32 && NA < 32 && NA <= MG, "one lane per row / column");
+    static_assert(MG * (NA + 33) <= HAREA + NA * 32, "the staged copy of [G | b] must fit the H and W areas");
 #pragma unroll 1
     for (int k = 0; k < NA; k++) {
       double* rb = vb + (k & 1) * 34;

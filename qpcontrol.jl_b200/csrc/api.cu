@@ -534,6 +534,7 @@ static int warp_shape(const DevProgram& p) {
   if (!on || p.nbx < 1 || p.nbx > 32) return 0;
   const int na = p.n - p.nbx;
   if (p.mg == 24 && na == 21) return 2421;  // StandingController on a humanoid with two feet (standing.jl:31-50)
+  if (p.mg == 30 && na == 27) return 3027;  // ... plus one weighted 6-row task (e.g. a hand driven by an SE3PDController)
   return 0;
 }
 static bool paa_is_diagonal(const DevProgram& p) {
@@ -567,6 +568,7 @@ static cudaError_t launch_warp(int shape, const Settings& st, const QpBuffers& q
                                long long B, int paa_diag, int* fb_list, int* fb_count, double* dbg, cudaStream_t stream) {
   switch (shape) {
     case 2421: return launch_warp_t<24, 21>(st, qb, n, nbx, base, B, paa_diag, fb_list, fb_count, dbg, stream);
+    case 3027: return launch_warp_t<30, 27>(st, qb, n, nbx, base, B, paa_diag, fb_list, fb_count, dbg, stream);
     default: return cudaErrorInvalidValue;
   }
 }

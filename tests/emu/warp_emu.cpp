@@ -166,7 +166,8 @@ int emu_warp_solve_qp_batch(int64_t B, int32_t n, int32_t mg, int32_t nbx, const
                             double adaptive_rho_tolerance, double kappa, double growth, int32_t first, int32_t check, int32_t aitken,
                             int32_t paa_diag, int32_t warm, double* x, double* y, double* rho_io, int32_t* status,
                             int32_t* iters, double* res, int32_t* nfac, int32_t* fallback, double* dbg) {
-  if (!(mg == 24 && n - nbx == 21 && nbx >= 1 && nbx <= 32)) return -1;
+  const bool s2421 = mg == 24 && n - nbx == 21, s3027 = mg == 30 && n - nbx == 27;
+  if (!((s2421 || s3027) && nbx >= 1 && nbx <= 32)) return -1;
   Settings st;
   memset(&st, 0, sizeof(st));
   st.rho = rho;
@@ -188,7 +189,7 @@ int emu_warp_solve_qp_batch(int64_t B, int32_t n, int32_t mg, int32_t nbx, const
   wp.first = first;
   wp.check = check;
   wp.aitken = aitken;
-  std::vector<double> smem(WarpSolver<24, 21>::SMEM_DOUBLES + 8);
+  std::vector<double> smem((s2421 ? WarpSolver<24, 21>::SMEM_DOUBLES : WarpSolver<30, 27>::SMEM_DOUBLES) + 8);
   for (int64_t i = 0; i < B; i++) {
     Job job;
     job.st = &st;
@@ -217,7 +218,7 @@ int emu_warp_solve_qp_batch(int64_t B, int32_t n, int32_t mg, int32_t nbx, const
       pb.x0 = pb.x;
       pb.y0 = pb.y;
     }
-    fallback[i] = run_warp<24, 21>(job);
+    fallback[i] = s2421 ? run_warp<24, 21>(job) : run_warp<30, 27>(job);
     if (fallback[i]) status[i] = QPC_WARP_FALLBACK;
   }
   return 0;

@@ -427,3 +427,27 @@ def test_thread_per_instance_tick_generic_dimensions(orc, variant):
     assert dev.launch_count() - n0 == 1  # below 4096 instances: one chunk, ONE kernel for the whole tick
     ref = orc.OracleController(low.program).solve_batch(q, v, desired=desired)
     parity.assert_tick_parity(res, ref, low.program)
+
+
+def test_warp_kernel_second_shape_vs_oracle(orc):
+    """qpc_admm_warp_kernel<30, 27>: the standing program plus one weighted 6-row SpatialAccelerationTask (the shape of a
+    standing controller with an SE3PD-driven hand) takes the one-warp kernel too; 1,024 states against the oracle at the
+    test-suite settings, and against the register-tile kernel's iteration counts to show which solver ran."""
+    from qpcontrol_jl_b200 import SpatialAccelerationTask
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    hand = list(mech.names).index("r_hand")
+    ti = low.addtask(SpatialAccelerationTask(mech, -1, hand, hand), 5.0)
+    off = low.program.des_offsets()[ti]
+    B = 1024
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=9)
+    des = np.tile(low.program.default_desired(), (B, 1))
+    des[:, off:off + 6] = np.random.default_rng(9).normal(0.0, 0.5, (B, 6))
+    dev = low.finalize()
+    assert dev.admm_warp()
+    res = low(q, v, des, check=False)
+    ref = orc.OracleController(low.program).solve_batch(q, v, desired=des)
+    parity.assert_tick_parity(res, ref, low.program)
+    dev.set_admm_warp(False)
+    reg = low(q, v, des, check=False)
+    dev.set_admm_warp(True)
+    assert res.iters.mean() < 0.6 * reg.iters.mean()  # the reduced problem with per-row rho needs far fewer iterations

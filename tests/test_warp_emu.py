@@ -125,3 +125,24 @@ def test_warm_start_from_the_solution_stops_at_the_first_check():
     assert np.all(cold["rho"] > 0)
     assert warm["iters"].max() <= 10 and warm["iters"].mean() < cold["iters"].mean() / 4
     assert np.abs(warm["x"] - cold["x"]).max() < 1e-2 * max(1.0, np.abs(cold["x"]).max())
+
+
+def test_second_shape_standing_plus_weighted_hand_task(orc):
+    """The (MG, NA) = (30, 27) instantiation: the standing program plus one weighted 6-row SpatialAccelerationTask (a hand,
+    as an SE3PDController would drive it): six more slack variables and six more equality rows in the block the QR
+    eliminates.  Tick through the warp body vs the oracle at the test-suite settings."""
+    from qpcontrol_jl_b200 import SpatialAccelerationTask
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.test_suite())
+    hand = list(mech.names).index("r_hand")
+    ti = low.addtask(SpatialAccelerationTask(mech, -1, hand, hand), 5.0)
+    off = low.program.des_offsets()[ti]
+    B = 16
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=9)
+    des = np.tile(low.program.default_desired(), (B, 1))
+    des[:, off:off + 6] = np.random.default_rng(9).normal(0.0, 0.5, (B, 6))
+    ec = emu.EmuController(low.program)
+    assert (ec.h.mg, ec.h.n - ec.h.nbox) == (30, 27)
+    res = ec.solve_warp(q, v, des)
+    ref = orc.OracleController(low.program).solve_batch(q, v, desired=des)
+    assert np.all(res.fallback == 0) and np.all(res.status == 1)
+    parity.assert_tick_parity(res, ref, low.program)
