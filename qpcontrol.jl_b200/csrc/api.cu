@@ -96,7 +96,7 @@ qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb,
     kin_contacts(pg, s);
     const int n = pg->n, mg = pg->mg, nbx = pg->nbx;
     kin_assemble(pg, s, qb.P + inst * n * n, qb.qv + inst * n, qb.G + inst * mg * n, qb.lg + inst * mg,
-                 qb.ug + inst * mg, qb.lb + inst * nbx, qb.ub + inst * nbx);
+                 qb.ug + inst * mg, qb.lb + inst * nbx, qb.ub + inst * nbx, qb.prezeroed != 0);
     for (int i = threadIdx.x; i < pg->ndes; i += blockDim.x) qb.des[inst * pg->ndes + i] = s.des[i];
     if (qb.ksave) kin_save(pg, s, qb.ksave + inst * kin_save_doubles(pg->nb, pg->nv, pg->ncontacts, pg->N));
     __syncthreads();
@@ -298,6 +298,9 @@ static int ensure_capacity(qpc_controller* c, long long B, long long dstride, lo
     CUDA_TRY(grow(b.P, B * n * n));
     CUDA_TRY(grow(b.qv, B * n));
     CUDA_TRY(grow(b.G, B * mg * n));
+    // zeroed once: the assembly kernel is their only writer and writes a static pattern (QpBuffers::prezeroed)
+    if (n > 0) CUDA_TRY(cudaMemset(b.P, 0, sizeof(double) * (size_t)(B * n * n)));
+    if (n > 0 && mg > 0) CUDA_TRY(cudaMemset(b.G, 0, sizeof(double) * (size_t)(B * mg * n)));
     CUDA_TRY(grow(b.lg, B * mg));
     CUDA_TRY(grow(b.ug, B * mg));
     CUDA_TRY(grow(b.lb, B * nbx));
@@ -638,6 +641,7 @@ static int ensure_time(qpc_controller* c, long long B) {
 static QpBuffers qp_view(const DeviceBuffers& b) {
   QpBuffers q;
   q.P = b.P;
+  q.prezeroed = 1;
   q.qv = b.qv;
   q.G = b.G;
   q.lg = b.lg;
@@ -1455,6 +1459,7 @@ int qpc_assemble_batch(qpc_controller* c, int64_t B, const qpc_batch_in* in, dou
     rc = stage_tick_parameters(c, B, in, false, false, io, s);
     if (rc) return rc;
     QpBuffers qb = qp_view(b);
+    qb.prezeroed = 0;  // the caller's arrays
     qb.P = P;
     qb.qv = qv;
     qb.G = G;

@@ -30,7 +30,7 @@ qpc_assemble_warp_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffer
     kin_contacts(pg, s);
     const int n = pg->n, mg = pg->mg, nbx = pg->nbx;
     kin_assemble(pg, s, qb.P + inst * n * n, qb.qv + inst * n, qb.G + inst * mg * n, qb.lg + inst * mg,
-                 qb.ug + inst * mg, qb.lb + inst * nbx, qb.ub + inst * nbx);
+                 qb.ug + inst * mg, qb.lb + inst * nbx, qb.ub + inst * nbx, qb.prezeroed != 0);
     for (int i = threadIdx.x; i < pg->ndes; i += blockDim.x) qb.des[inst * pg->ndes + i] = s.des[i];
     if (qb.ksave) kin_save(pg, s, qb.ksave + inst * kin_save_doubles(pg->nb, pg->nv, pg->ncontacts, pg->N));
     QPC_SYNC();

@@ -137,6 +137,8 @@ struct QpBuffers {
   int* nfac;    // [B] number of factorisations (1 + rho updates), optional
   double* rho;  // [B] final rho of the slot's last accepted solve (<= 0: none); read when `warm`
   double* ksave = nullptr;  // [B][kin_save_doubles] kinematic state handed from the assembly to the inverse-dynamics kernel
+  int prezeroed = 0;  // P and G were zeroed when the workspace was allocated and only the assembly kernel writes them: the
+                      // structurally zero entries (a static pattern of the program) need no per-tick clearing
   int warm;     // OSQP's implicit warm start: start from x, y, rho of the previous tick of the same slot
   // list mode (the instances the one-warp kernel handed back): solve instances list[0 .. *list_count) only, on a
   // bounded persistent grid of list_grid CTAs
