@@ -280,8 +280,11 @@ struct WarpSolver {
   }
 
   // dbg (optional, instance `base` only): H [1024] h [32] A3 [ME*32] b3 [ME] xa0 [NA] W [NA*32] cs
+  // pflags: bit 0 = P_aa is diagonal; bits 8.. = block size of a block-diagonal P_bb (the controller's contact cost
+  // 2 w_c B'B couples only the N multipliers of one contact point; 0 = dense)
   static __device__ void solve(const Settings& st, const WarpParams& wp, const AdmmProblem& pb, int n, int nbx,
-                               int paa_diag, double* sm, int& fallback, double* dbg) {
+                               int pflags, double* sm, int& fallback, double* dbg) {
+    const int paa_diag = pflags & 1, pbb_block = pflags >> 8;
     const int lane = threadIdx.x & 31;
     const int na = NA;
     fallback = 0;  // reason code when the instance is handed back: 1 bounds, 2 rank of G_a, 3 rank of A3, 4 cost scale,
@@ -572,6 +575,17 @@ struct WarpSolver {
     // column i of every lane's row
     {
       const double* pp = pb.P + (size_t)na * n + na + lane;
+      if (pbb_block > 0) {
+        // block-diagonal P_bb: the lane's column has entries only in the rows of its own contact point -- N loads instead
+        // of 32 (1 KB instead of 8 KB of P read per solve)
+        const int b0 = (lane / pbb_block) * pbb_block;
+        if (hasb) {
+#pragma unroll 1
+          for (int i = b0; i < b0 + pbb_block && i < nbx; i++) Hs[i * 32 + lane] += pp[(size_t)i * n];
+        } else {
+          Hs[lane * 32 + lane] += 1.0;
+        }
+      } else
 #pragma unroll 1
       for (int i0 = 0; i0 < 32; i0 += QPC_WARP_PBATCH) {  // QPC_WARP_PBATCH loads in flight before the first use
         double pv[QPC_WARP_PBATCH];

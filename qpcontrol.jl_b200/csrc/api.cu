@@ -545,6 +545,13 @@ static bool paa_is_diagonal(const DevProgram& p) {
     if (!p.tasks[i].eliminated && p.tasks[i].mode == 2) return false;
   return true;
 }
+// structure flags of the assembled P for the one-warp kernel (admm_warp.cuh: solve): P_aa diagonal; P_bb block diagonal
+// with one N x N block per contact point (contacts.jl:75-79: the cost couples only the multipliers of one point)
+static int warp_pflags(const DevProgram& p) {
+  bool blocks = p.ncontacts > 0 && p.nbx == p.ncontacts * p.N;
+  for (int c = 0; c < p.ncontacts && blocks; c++) blocks = p.contacts[c].col0 == (p.n - p.nbx) + c * p.N;
+  return (paa_is_diagonal(p) ? 1 : 0) | ((blocks ? p.N : 0) << 8);
+}
 template <int MG, int NA>
 static cudaError_t launch_warp_t(const Settings& st, const QpBuffers& qb, int n, int nbx, long long base, long long B,
                                  int paa_diag, int* fb_list, int* fb_count, double* dbg, cudaStream_t stream) {
@@ -764,7 +771,7 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
           CUDA_TRY(cudaMalloc((void**)&dbg, sizeof(double) * ndbg));
           CUDA_TRY(cudaMemset(dbg, 0, sizeof(double) * ndbg));
         }
-        CUDA_TRY(launch_warp(wshape, p.settings, qb, p.n, p.nbx, lo, hi, paa_is_diagonal(p) ? 1 : 0, c->be.d_fb_list + lo,
+        CUDA_TRY(launch_warp(wshape, p.settings, qb, p.n, p.nbx, lo, hi, warp_pflags(p), c->be.d_fb_list + lo,
                              cnt, dbg, s));
         if (dbg) {
           std::vector<double> hd(ndbg);

@@ -52,6 +52,7 @@ class EmuController:
         and inverse-dynamics stages; `fallback` (reason codes) is attached to the result."""
         h = self.h
         a = self.assemble(q, v, desired, cw, cm)
+        warp_kw.setdefault("pbb_block", h.program.N)  # the product passes the contact-block structure of P (api.cu: warp_pflags)
         w = warp_solve_qp_batch(a["P"], a["q"], a["G"], a["lg"], a["lb"], a["ub"], settings=h.program.settings, **warp_kw)
         h.sync_defaults()
         q, v, desired, cw, cm, B = L._prep_host_inputs(h, q, v, desired, cw, cm)
@@ -127,7 +128,7 @@ def build_warp():
     return _WSO
 
 
-def warp_solve_qp_batch(P, qv, G, lg, lb, ub, settings=None, kappa=30.0, growth=1.35, first=25, check=5, aitken=25, paa_diag=True,
+def warp_solve_qp_batch(P, qv, G, lg, lb, ub, settings=None, kappa=30.0, growth=1.35, first=25, check=5, aitken=25, paa_diag=True, pbb_block=0,
                         warm=None, debug=False):
     """The one-warp ADMM kernel body (csrc/admm_warp.cuh, MG = 24, NA = 21) run on 32 CPU fibres per QP."""
     lib = C.CDLL(build_warp())
@@ -147,7 +148,7 @@ def warp_solve_qp_batch(P, qv, G, lg, lb, ub, settings=None, kappa=30.0, growth=
                                      C.c_double(st.eps_rel), C.c_double(st.eps_prim_inf), C.c_int32(st.max_iter),
                                      C.c_int32(int(st.adaptive_rho)), C.c_double(st.adaptive_rho_tolerance),
                                      C.c_double(kappa), C.c_double(growth), C.c_int32(first), C.c_int32(check), C.c_int32(aitken),
-                                     C.c_int32(int(paa_diag)), C.c_int32(0 if warm is None else 1), p(out["x"]),
+                                     C.c_int32(int(paa_diag) | (int(pbb_block) << 8)), C.c_int32(0 if warm is None else 1), p(out["x"]),
                                      p(out["y"]), p(out["rho"]), p(out["status"]), p(out["iters"]), p(out["res"]),
                                      p(out["nfac"]), p(out["fallback"]), p(out["dbg"]) if debug else None)
     if rc != 0:
