@@ -15,7 +15,9 @@ rank owns its own contiguous block of instances (seed offset by rank); nothing i
 `value`     solves/s with the inputs resident in HBM, timed with CUDA events on the launching stream (per step, L2
             flushed between steps), max over ranks.
 `e2e`       the same metric through the reference-facing call with HOST buffers (qpc_solve_batch, QPC_HOST_PTRS):
-            pinned host q/v in, tau/vdot/wrenches/status/iters/residuals out, copies inside the timed region.
+            pinned host q/v in, tau/vdot/wrenches/status/iters/residuals out, all transfers inside the timed region
+            (inputs and the small outputs by chunked async copies; tau/vdot/wrenches are written into the pinned output
+            buffers by the epilogue kernel itself -- the same bytes over PCIe, counted in d2h_bytes_per_step).
 `roofline`  dominant kernel (the ADMM solve; the one-warp-per-QP kernel for the standing program): the FLOPs its
             algorithm executes (reduction + R inversions + K iterations, 2 per FMA) x batch / its
             CUDA-event duration, against the fp64 DFMA peak measured live on the same device.  SURVEY.md 8(d)'s
