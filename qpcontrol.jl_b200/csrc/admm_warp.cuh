@@ -648,10 +648,19 @@ struct WarpSolver {
     int status = -10, iter = 0;
     int next_adapt = (adaptive && wp.first > 0) ? wp.first : 0x7fffffff;
     const int chk = wp.check > 0 ? wp.check : 0x7fffffff;
-    int next_chk = chk;
+    // warm-started solves (closed loop near a fixed point, restarts from a solution) often need a handful of iterations:
+    // they get dense checks (every 5) up to the first full check at 25; cold solves only pay for checks that can succeed
+    const int chk_early = min(chk, 5);
+    int next_chk = warm ? chk_early : chk;
+    // iterations that take the full check whatever `chk` is: multiples of 25 (infeasibility test) and of the extrapolation
+    // interval; `next_full` = the next of them
+    const int ait = wp.aitken > 0 ? wp.aitken : 0x7fffffff;
+    auto full_after = [&](int it) { return min((it / 25 + 1) * 25, ait < 0x7fffffff ? (it / ait + 1) * ait : 0x7fffffff); };
+    int next_full = full_after(0);
     const double alpha = st.alpha, oma = 1.0 - st.alpha;
     double pri_res = 0.0, dua_res = 0.0, xt = 0.0;
     double ds_last = 1e300;  // last evaluated dual normaliser max(|Px|, |A'y|, |q|)
+    double ps_last = 1e300;  // primal normaliser max(|Ax|, |z|) of the last full check (1e300: none yet)
     double rp_last = -1.0;   // primal residual at the previous adaptation point
     bool refactor = true;
     int hist = 0;            // extrapolation history: 0 none, 1 a previous point, 2 also a previous increment
@@ -667,7 +676,7 @@ struct WarpSolver {
         }
       }
       // plain iterations up to the next special one
-      const int stop = min(min(next_chk, next_adapt), st.max_iter);
+      const int stop = min(min(min(next_chk, next_full), next_adapt), st.max_iter);
 #pragma unroll 1
       for (; iter < stop - 1; iter++) {
         double* ub_ = vb + (iter & 1) * 34;
@@ -701,6 +710,16 @@ struct WarpSolver {
       const bool adapt = iter == next_adapt, last = iter >= st.max_iter;
       const double dy = rho_i * (yr - yro);
       const double rdv = dy - rho_i * (xt - zo);  // = H x~ + h + A3'nu + y+ : stationarity defect of the x_b rows
+      // Quick reject at the dense check points (one vote instead of four warp maxima and the bookkeeping of a full check):
+      // against the normalisers of the last full check, with slack for their drift, a lane whose own residual is above the
+      // tolerance proves "not converged".  It can only delay a termination to the next full check (every 25th iteration,
+      // the extrapolation and adaptation points), never cause one.
+      if (!adapt && !last && iter != next_full &&
+          __any_sync(FULL, fabs(xt - z) >= st.eps_abs + st.eps_rel * 2.0 * ps_last ||
+                               fabs(rdv) >= st.eps_abs + st.eps_rel * 8.0 * ds_last)) {
+        next_chk = iter + ((warm && iter < 25) ? chk_early : chk);
+        continue;
+      }
       pri_res = wmax(xt - z);
       dua_res = wmax(rdv);
       if (!finite_val(pri_res) || !finite_val(dua_res)) {
@@ -709,6 +728,7 @@ struct WarpSolver {
       }
       const double xzmax = fmax(wmax(xt), wmax(z));
       const double ps = fmax(bn, xzmax);
+      ps_last = ps;
       const bool pok = pri_res < st.eps_abs + st.eps_rel * ps;
       bool done = false;
       if (pok && dua_res < st.eps_abs) {
@@ -799,7 +819,8 @@ struct WarpSolver {
         done = true;
       }
       if (done) break;
-      if (iter == next_chk) next_chk += chk;
+      if (iter == next_chk) next_chk += (warm && iter < 25) ? chk_early : chk;
+      if (iter == next_full) next_full = full_after(iter);
       if (adapt) {
         // schedule: every `first` iterations early on, then geometric (x growth): solves that need several re-weightings of
         // their rows get them quickly (they used to sit out the gaps of a x2 schedule: 410 iterations instead of 150),

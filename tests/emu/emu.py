@@ -128,7 +128,7 @@ def build_warp():
     return _WSO
 
 
-def warp_solve_qp_batch(P, qv, G, lg, lb, ub, settings=None, kappa=30.0, growth=1.35, first=25, check=5, aitken=25, paa_diag=True, pbb_block=0,
+def warp_solve_qp_batch(P, qv, G, lg, lb, ub, settings=None, kappa=30.0, growth=1.35, first=25, check=25, aitken=25, paa_diag=True, pbb_block=0,
                         warm=None, debug=False):
     """The one-warp ADMM kernel body (csrc/admm_warp.cuh, MG = 24, NA = 21) run on 32 CPU fibres per QP."""
     lib = C.CDLL(build_warp())
