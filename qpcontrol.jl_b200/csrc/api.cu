@@ -2,6 +2,7 @@
 // Built for sm_100a only:  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ...   (see Makefile)
 #include <cuda_runtime.h>
 
+#include <array>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -748,7 +749,12 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
     const bool kwarp = kin_warp_per_instance(p, ksm);
     if (kwarp) CUDA_TRY(kin_warp_assemble(dp, io, qb, lo, hi, ksm, s, p.nse3 > 0));
     else if (p.nse3) qpc_assemble_kernel<true><<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
-    else qpc_assemble_kernel<false><<<grid, ASM_THREADS, ksm, s>>>(dp, io, qb, lo, hi);
+    else {
+      // QPC_ASM_PAD_SMEM=<bytes>: development knob (occupancy scan of the assembly kernel)
+      static const int pad = [] { const char* e = getenv("QPC_ASM_PAD_SMEM"); return e ? atoi(e) : 0; }();
+      if (pad) cudaFuncSetAttribute(qpc_assemble_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ksm + pad);
+      qpc_assemble_kernel<false><<<grid, ASM_THREADS, ksm + pad, s>>>(dp, io, qb, lo, hi);
+    }
     if (timed) cudaEventRecord(c->be.ev[1], s);
     if (p.n > 0) {
       // Fast path with the diagonal-cost free variables eliminated: only for tolerances above the floor that form puts
@@ -840,7 +846,12 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
     // those two chunks are smaller (15 % of the batch each with four chunks)
     auto cut = [&](int k) -> long long {
       if (!hx || nchunk != 4) return B * k / nchunk;
-      static const double frac[5] = {0.0, 0.15, 0.5, 0.85, 1.0};
+      // QPC_CHUNK_FRACS="a,b,c": development knob for the three inner cut points
+      static const std::array<double, 5> frac = [] {
+        std::array<double, 5> f = {0.0, 0.15, 0.5, 0.85, 1.0};
+        if (const char* e = getenv("QPC_CHUNK_FRACS")) sscanf(e, "%lf,%lf,%lf", &f[1], &f[2], &f[3]);
+        return f;
+      }();
       return k == nchunk ? B : (long long)(B * frac[k]);
     };
     for (int k = 0; k < nchunk; k++) {
