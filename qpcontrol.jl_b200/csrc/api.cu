@@ -83,8 +83,11 @@ constexpr int ID_THREADS = QPC_KIN_THREADS;
 
 // SE3: programs with device-side SE3PDControllers (kin_se3pd); a separate instantiation so that the evaluator's registers
 // stay out of the kernel every other program runs (one shared kernel cost the Atlas standing tick 0.18 ms in spills)
+#ifndef QPC_ASM_MIN_CTAS
+#define QPC_ASM_MIN_CTAS 10  // register budget of the plain instantiation: 96 registers (shared memory admits nine CTAs per SM)
+#endif
 template <bool SE3>
-__global__ void __launch_bounds__(ASM_THREADS)
+__global__ void __launch_bounds__(ASM_THREADS, SE3 ? 1 : QPC_ASM_MIN_CTAS)
 qpc_assemble_kernel(const DevProgram* __restrict__ pg, BatchIO io, QpBuffers qb, long long base, long long B) {
   extern __shared__ double smem[];
   for (long long inst = base + blockIdx.x; inst < B; inst += gridDim.x) {

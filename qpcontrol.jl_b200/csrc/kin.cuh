@@ -24,12 +24,17 @@ struct KinSmem {
   const double* wm;                     // matrix weights of this tick (Wbuf layout): the per-tick Parameter or pg->Wbuf
   double *ct;                           // per contact (kin_ct_stride): z_up rotation 9, position 3, B 3N, B'B N^2, maxrho factor
 };
-QPC_HD int kin_ct_stride(int N) { return 13 + 3 * N + N * N; }
+// per contact: z_up rotation 9, position 3, force basis B 3N, maxrho factor 1 (B'B is formed where it is used)
+QPC_HD int kin_ct_stride(int N) { return 13 + 3 * N; }
 
+// Shared memory per instance bounds the resident instances per SM of the assembly kernel: the task-row buffer Jt shares the
+// composite-inertia area (dead once the momentum matrix exists) and B'B is not staged -- 22.3 KB instead of 25.1 KB for
+// Atlas, nine CTAs per SM instead of eight (measured: 7 -> 8 CTAs was worth 9 %, 8 -> 9 nothing).
+QPC_HD int kin_ic_doubles(int nb, int nv) { return 10 * nb > 6 * nv ? 10 * nb : 6 * nv; }
 QPC_HD int kin_smem_doubles(int nb, int nq, int nv, int ndes, int nc, int N) {
   const int na = nv > nc ? nv : nc;
-  return nq + nv + ndes + 2 * nc + nb * (12 + 6 + 6 + 10 + 10) + nv * 6 + nb * 12 + 24 + 6 * na + nc * N * 6 + 6 * nv +
-         16 + 8 + QPC_MAXT + nc * (13 + 3 * N + N * N);
+  return nq + nv + ndes + 2 * nc + nb * (12 + 6 + 6 + 10) + kin_ic_doubles(nb, nv) + nv * 6 + nb * 12 + 24 + 6 * na +
+         nc * N * 6 + 16 + QPC_MAXT + nc * kin_ct_stride(N);
 }
 QPC_HD KinSmem kin_layout(double* b, int nb, int nq, int nv, int ndes, int nc, int N) {
   KinSmem s;
@@ -42,16 +47,15 @@ QPC_HD KinSmem kin_layout(double* b, int nb, int nq, int nv, int ndes, int nc, i
   s.TW = b;     b += nb * 6;
   s.BI = b;     b += nb * 6;
   s.IW = b;     b += nb * 10;
-  s.IC = b;     b += nb * 10;
+  s.IC = b;     s.Jt = b;  b += kin_ic_doubles(nb, nv);  // Jt (6 nv) is first written after the last read of IC
   s.SW = b;     b += nv * 6;
   s.scr = b;    b += nb * 12;
   s.tot = b;    b += 24;
   s.A = b;      b += 6 * (nv > nc ? nv : nc);
   s.GC = b;     b += nc * N * 6;
-  s.Jt = b;     b += 6 * nv;
   s.bt = b;     b += 16;
   s.tw = b;     b += QPC_MAXT;
-  s.ct = b;     b += nc * (13 + 3 * N + N * N);
+  s.ct = b;     b += nc * kin_ct_stride(N);
   return s;
 }
 
@@ -140,8 +144,7 @@ QPC_DEV void kin_load(const DevProgram* __restrict__ pg, const BatchIO& io, long
       for (int i = 0; i < 9; i++) ct[i] = dc.Rz[i];
       for (int i = 0; i < 3; i++) ct[9 + i] = dc.pos[i];
       for (int i = 0; i < 3 * N; i++) ct[12 + i] = dc.B[i];
-      for (int i = 0; i < N * N; i++) ct[12 + 3 * N + i] = dc.BtB[i];
-      ct[12 + 3 * N + N * N] = dc.maxrho_factor;
+      ct[12 + 3 * N] = dc.maxrho_factor;
     } else {
       const double* gq = io.cgeom + inst * io.cgeom_stride + 7 * c;
       const double mu = gq[6];
@@ -156,10 +159,7 @@ QPC_DEV void kin_load(const DevProgram* __restrict__ pg, const BatchIO& io, long
         B[N + g] = b.y * inv;
         B[2 * N + g] = b.z * inv;
       }
-      for (int a = 0; a < N; a++)
-        for (int b = 0; b < N; b++)
-          ct[12 + 3 * N + a * N + b] = B[a] * B[b] + B[N + a] * B[N + b] + B[2 * N + a] * B[2 * N + b];
-      ct[12 + 3 * N + N * N] = 1.0 / (N * sqrt(mu * mu + 1.0));  // contacts.jl:57
+      ct[12 + 3 * N] = 1.0 / (N * sqrt(mu * mu + 1.0));  // contacts.jl:57
     }
   }
   QPC_SYNC();
@@ -553,12 +553,13 @@ QPC_DEV void kin_assemble(const DevProgram* __restrict__ pg, KinSmem& s, double*
   for (int k = t0; k < pg->ncontacts * N * N; k += nt) {
     const int c = k / (N * N), a = (k / N) % N, b = k % N;
     const DevContact& dc = pg->contacts[c];
-    P[(dc.col0 + a) * n + dc.col0 + b] = 2.0 * s.cw[c] * s.ct[c * kin_ct_stride(N) + 12 + 3 * N + a * N + b];
+    const double* Bc = s.ct + c * kin_ct_stride(N) + 12;  // B'B of the contact's force basis (contacts.jl:75-79)
+    P[(dc.col0 + a) * n + dc.col0 + b] = 2.0 * s.cw[c] * (Bc[a] * Bc[b] + Bc[N + a] * Bc[N + b] + Bc[2 * N + a] * Bc[2 * N + b]);
   }
   for (int k = t0; k < pg->ncontacts * N; k += nt) {
     const int c = k / N;
     lb[k] = 0.0;
-    ub[k] = s.cm[c] * s.ct[c * kin_ct_stride(N) + 12 + 3 * N + N * N];
+    ub[k] = s.cm[c] * s.ct[c * kin_ct_stride(N) + 12 + 3 * N];
   }
   QPC_SYNC();
   // Task rows, software-pipelined over two (Jt, bt) buffers: in one barrier interval the threads produce task j's rows
