@@ -72,17 +72,58 @@ def algorithmic_flops(n, m, K, R):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every ~3 ms through NVML (in-process thread) while the warm-up and the timed
+    region run -- the timed region is tens of milliseconds, shorter than the start-up of an nvidia-smi process; nvidia-smi
+    (-lms 20) is the fallback when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.rows = []
+
+    def _nvml_loop(self, nv, handle):
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.rows.append((float(sm), int(mask)))
+            except Exception:
+                pass
+            time.sleep(0.003)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber the devices: go through the PCI bus id of the torch device
+            import torch
+            bus = getattr(torch.cuda.get_device_properties(self.gpu), "pci_bus_id", None)
+            handle = None
+            if bus is not None:
+                for i in range(nv.nvmlDeviceGetCount()):
+                    h = nv.nvmlDeviceGetHandleByIndex(i)
+                    if nv.nvmlDeviceGetPciInfo(h).bus == bus:
+                        handle = h
+                        break
+            if handle is None:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self._stop = False
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(prefix="qpc_clocks_", suffix=".csv")
             os.close(fd)
@@ -95,6 +136,14 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            if self.rows:
+                reasons = sorted({nm for _, mask in self.rows for bit, nm in self.REASONS if mask & bit})
+                out.update(sm_mhz=float(np.median([r[0] for r in self.rows])), sm_max_mhz=self.smax, reasons=reasons,
+                           samples=len(self.rows), source="nvml")
+            return out
         if self.proc is None:
             return out
         try:
@@ -123,7 +172,7 @@ class ClockSampler:
                     reasons.add(nm)
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
-                       samples=len(sm))
+                       samples=len(sm), source="nvidia-smi")
         return out
 
 
