@@ -62,11 +62,13 @@ def bench_settings_accuracy(n):
     oc.reset()
     loose = oc.solve_batch(q, v)
     dev = low.finalize()
-    fast = ctrl(q, v, check=False)
+    fast = ctrl(q, v, check=False)          # the default solver: the one-warp kernel on the reduced problem
     nel = dev.admm_eliminated()
     dev.set_admm_elimination(False)
-    full = ctrl(q, v, check=False)
+    dev.set_admm_warp(False)
+    full = ctrl(q, v, check=False)          # the register-tile kernel on the full KKT system (round 1's formulation)
     dev.set_admm_elimination(True)
+    dev.set_admm_warp(True)
     ok = (truth["status"] == 1) & ((fast.status == 1) | (fast.status == 2)) & ((full.status == 1) | (full.status == 2)) & \
         ((loose["status"] == 1) | (loose["status"] == 2))
 
@@ -78,8 +80,9 @@ def bench_settings_accuracy(n):
     return {"instances": int(n), "compared": int(ok.sum()), "eliminated_variables": int(nel),
             "settings": "eps_abs = eps_rel = 1e-5, max_iter 5000 (Standing controller.ipynb:66-71), cold start",
             "reference": "oracle at eps_abs 1e-8 / eps_rel 1e-16 (test/runtests.jl:35-43)",
-            "device_fast_path": dict(stats(fast.tau, fast.wrenches), iters_mean=float(fast.iters.mean())),
-            "device_full_system": dict(stats(full.tau, full.wrenches), iters_mean=float(full.iters.mean())),
+            "device_default_solver": dict(stats(fast.tau, fast.wrenches), iters_mean=float(fast.iters.mean()),
+                                          one_warp_kernel=bool(dev.admm_warp())),
+            "device_kkt_register_tile_kernel": dict(stats(full.tau, full.wrenches), iters_mean=float(full.iters.mean())),
             "cpu_oracle_same_settings": dict(stats(loose["tau"], loose["wrenches"]), iters_mean=float(loose["iters"].mean())),
             "accept_reject_fast_vs_full_identical": bool(np.array_equal((fast.status == 1) | (fast.status == 2),
                                                                         (full.status == 1) | (full.status == 2)))}
