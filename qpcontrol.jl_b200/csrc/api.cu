@@ -839,7 +839,10 @@ static int run_tick(qpc_controller* c, long long B, const BatchIO& io, double* t
   // Large batches are cut into NSIDE contiguous chunks on side streams (forked from / joined to the caller's stream):
   // the GPU then overlaps chunk k's inverse dynamics, chunk k+1's assembly and the tail of chunk k's ADMM kernel with
   // the bulk of the next ADMM kernel.  Results do not depend on the chunking (instances are independent).
-  const int nchunk = (!prof && B >= 4096 && c->be.side[0]) ? Backend::NSIDE : 1;
+  // QPC_NCHUNK=<n>: development knob (1 .. NSIDE)
+  static const int nchunk_env = [] { const char* e = getenv("QPC_NCHUNK"); return e ? atoi(e) : 0; }();
+  int nchunk = (!prof && B >= 4096 && c->be.side[0]) ? Backend::NSIDE : 1;
+  if (nchunk > 1 && nchunk_env >= 1 && nchunk_env <= Backend::NSIDE) nchunk = nchunk_env;
   if (nchunk == 1) {
     int rc = tick_range(0, B, stream, prof, Backend::NSIDE);
     if (rc) return rc;
