@@ -102,3 +102,25 @@ def test_global_scratch_qp_path_does_not_allocate_in_steady_state():
     free1, _ = torch.cuda.mem_get_info()
     assert free1 == free0
     assert np.all(dstat.cpu().numpy() == 1)
+
+
+def test_direct_writes_into_pinned_outputs_equal_the_staged_copies():
+    """Page-locked OUTPUT buffers are written by the epilogue kernel itself (api.cu: mapped_alias); pageable ones go
+    through the staging buffer and a D2H copy per chunk.  Same bits, chunked path, odd batch."""
+    import torch
+    mech, low, ctrl, qnom = scenarios.atlas_standing(OSQPSettings.standing_notebook())
+    B = 5001
+    q, v = scenarios.atlas_random_states(mech, qnom, B, seed=19)
+    dev = low.finalize()
+    staged = dev.solve_host(q, v)  # fresh numpy arrays: pageable
+    h = dev.h
+    pin = lambda shape, dt=torch.float64: torch.empty(*shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+    from qpcontrol_jl_b200 import BatchResult
+    res = BatchResult(tau=pin((B, h.nv)), vdot=pin((B, h.nv)), wrenches=pin((B, h.ncontacts, 6)),
+                      status=pin((B,), torch.int32), iters=pin((B,), torch.int32), residuals=pin((B, 2)))
+    res.tau[:] = np.nan
+    res.wrenches[:] = np.nan
+    dev.solve_host_into(q, v, res)
+    assert np.array_equal(res.tau, staged.tau) and np.array_equal(res.vdot, staged.vdot)
+    assert np.array_equal(res.wrenches, staged.wrenches) and np.array_equal(res.status, staged.status)
+    assert np.array_equal(res.iters, staged.iters) and np.array_equal(res.residuals, staged.residuals)

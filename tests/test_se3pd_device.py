@@ -147,3 +147,22 @@ def test_closed_loop_advances_the_controller_time():
     assert np.array_equal(qa, qb) and np.array_equal(va, vb) and np.array_equal(ra.tau, rb.tau)
     qc, vc, rc = low.simulate(q1, v1, dt, 1, time=t0, check=False)  # wrong time: the result must differ
     assert not np.array_equal(rc.tau, rb.tau)
+
+
+@pytest.mark.gpu
+def test_trajectory_and_gains_are_refs_on_the_device():
+    """qpc_se3pd_update through the C ABI: replacing controller.trajectory / controller.gains between ticks re-uploads the
+    program tables; the desired the assembly kernel writes follows the host functor before and after the swap."""
+    mech, low, ctrl, qnom, se3, off = make("interpolated", True)
+    q, v = states(mech, qnom, 64, 6)
+    dev = low.finalize()
+    a = dev.assemble_host(q, v, time=0.8)["desired"][:, off:off + 6]
+    want_a = se3(0.8, mech, q, v)
+    assert np.max(np.abs(a - want_a)) <= 1e-9 * max(1.0, np.max(np.abs(want_a)))
+    se3.gains = SE3PDGains(PDGains(50.0, 5.0), PDGains(300.0, 30.0))
+    se3.trajectory = T.SE3Trajectory(se3.body, se3.base, T.Constant(quat([0, 1, 0], 0.4), rotation=True),
+                                     T.Interpolated(0.0, 2.0, np.zeros(3), np.ones(3)))
+    b = dev.assemble_host(q, v, time=0.8)["desired"][:, off:off + 6]
+    want_b = se3(0.8, mech, q, v)
+    assert np.max(np.abs(b - want_b)) <= 1e-9 * max(1.0, np.max(np.abs(want_b)))
+    assert np.max(np.abs(a - b)) > 1e-3
