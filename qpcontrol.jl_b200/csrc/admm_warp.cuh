@@ -5,7 +5,8 @@
 // Device-side replacement for `MOI.optimize!(::OSQP.Optimizer)` reached by `solve!(qpmodel)` (reference
 // src/lowlevel/momentum.jl:58) for controller programs whose general rows are all equalities and whose unboxed variables
 // x_a (free accelerations, task-error slacks: momentum.jl:28,119-126) are determined by those rows (NA <= MG, G_a of
-// full column rank) -- the StandingController's program (standing.jl:31-50) is the model case: NA = 21, MG = 24.
+// full column rank) -- the StandingController's program (standing.jl:31-50) is the model case: NA = 21, MG = 24
+// (api.cu also instantiates NA = 27, MG = 30: that program plus one weighted 6-row task).
 //
 // Instead of iterating on the (n + m)-dimensional KKT system, the warp first REDUCES the problem (once per solve):
 //   1. Householder QR of G_a applied to [G_a | G_b | b], one matrix column per lane, reflectors broadcast through
@@ -19,7 +20,8 @@
 //   4. An iteration = lane j's row of T (32 registers) times the vector u = z - y/rho read from shared memory as 16
 //      broadcast 16-byte loads: 32 DFMA per lane, NO cross-lane reduction, one __syncwarp, then relaxation / projection /
 //      dual update in the lane's registers.  The residuals of OSQP's termination test are lane-local quantities
-//      (primal: x~ - z; dual: the stationarity defect of the x-update, y+ - y - rho (x~ - z)) + two redux.sync maxima.
+//      (primal: x~ - z; dual: the stationarity defect of the x-update, y+ - y - rho (x~ - z)) + warp maxima by redux.sync,
+//      tested every 25 iterations (leaving the tight loop more often costs more than the iterations it saves).
 // Per-row rho (OSQP's rho_vec: equality rows get 1e3 rho) is extended to the active set: rows whose z sits on a bound
 // get kappa rho, interior rows rho / kappa, re-evaluated together with OSQP's residual-balancing rule on a geometric
 // schedule (iterations first, first growth, ...), so the number of refactorisations is bounded and the iteration is a
