@@ -842,6 +842,15 @@ struct WarpSolver {
         const bool big = stalled || rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance;
         const bool an = (z <= lo) || (z >= up);
         const bool changed = kap != 1.0 && __any_sync(FULL, an != act);
+#if defined(QPC_WARP_EMU) && defined(QPC_WARP_ADAPT_STATS)
+        {  // development statistics (tests/emu only): iteration, global change, rows that change their rho class
+          const int nch = __reduce_max_sync(FULL, 0) + 0;  // keep the fibres in step
+          (void)nch;
+          int cnt = 0;
+          for (int l = 0; l < 32; l++) cnt += (__shfl_sync(FULL, (double)(an != act), l) != 0.0) ? 1 : 0;
+          if (lane == 0) qpc_adapt_stats(iter, big ? 1 : 0, cnt);
+        }
+#endif
         if (big || changed) {
           if (big) rho = rn;
           act = an;
