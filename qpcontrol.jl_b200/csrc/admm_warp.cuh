@@ -46,6 +46,7 @@ struct WarpParams {
   int first;      // first adaptation iteration
   int check;      // residual check interval
   int aitken;     // extrapolation of slowly converging solves every this many iterations (0 = off)
+  double gather_eps;  // the inversion gathers its pivot rows by symmetry when eps_abs >= this (see WarpSolver::factor)
 };
 
 #if defined(__CUDACC__)
@@ -142,7 +143,7 @@ struct WarpSolver {
 
   // K = H + diag(rho) -> T~ = T diag(rho) in t[], t0; returns false on a non-positive pivot.  `rho_i` = this lane's rho.
   static __device__ __forceinline__ bool factor(double* sm, double (&t)[32], double& t0, double rho_i,
-                                                const double (&a3)[MEP], const double (&b3)[MEP], int lane) {
+                                                const double (&a3)[MEP], const double (&b3)[MEP], int lane, bool gather) {
     double* Hs = sm + OFF_H;
     double* vb = sm + OFF_V;
     // K = H + diag(rho): the lane's diagonal entry is bumped in shared memory around the load (only this lane reads it)
@@ -162,13 +163,23 @@ struct WarpSolver {
     // The reciprocal of the NEXT pivot is taken right after the first FMA of a step (register 0 of lane k + 1 is then
     // its diagonal entry) and travels with the pivot row: the ~60-cycle rcp chain overlaps the step's other 31 FMAs
     // instead of sitting between the broadcast and the multiplier of every step.
-    double s = 1.0;
+    // `gather`: the pivot row is GATHERED instead of broadcast.  K is symmetric and Gauss-Jordan keeps the working matrix
+    // symmetric up to sign (rows that have been pivot rows carry -(their column)), so row k is the column-k entry of every
+    // lane: one 8-byte store per lane -- f t[0], f = 1 before the lane's own pivot step, -(pending scale) after -- at the
+    // rotated position, instead of sixteen 16-byte stores of lane k's registers that 31 lanes issue predicated off: the ADMM
+    // stage of 16,384 solves 1.17 -> 1.01 ms.  Lane k keeps its own row, which equals the gathered one only up to the
+    // asymmetry the rounding errors have built up: fine at eps 1e-5, a floor on the residuals at 1e-8 (solves stalled at the
+    // iteration limit), so tight tolerances take the broadcast (WarpParams::gather_eps).
+    double s = 1.0, f = 1.0;
     bool ok = true;
     double dk_mine = rcp_pos(t[0]);
 #pragma unroll 1
     for (int k = 0; k < 32; k++) {
       double* rb = vb + (k & 1) * 34;
-      if (lane == k) {
+      if (gather) {
+        rb[(lane - k) & 31] = f * t[0];
+        if (lane == k) rb[32] = dk_mine;
+      } else if (lane == k) {
         double2* r2 = reinterpret_cast<double2*>(rb);
 #pragma unroll
         for (int c = 0; c < 16; c++) r2[c] = make_double2(t[2 * c], t[2 * c + 1]);
@@ -190,7 +201,10 @@ struct WarpSolver {
         t[2 * c] = fma(-m, p.y, t[2 * c + 1]);
       }
       t[31] = (lane == k) ? 1.0 : -m;
-      if (lane == k) s = dk;
+      if (lane == k) {
+        s = dk;
+        f = -dk;
+      }
     }
 #pragma unroll
     for (int i = 0; i < 32; i++) t[i] *= s;
@@ -669,7 +683,7 @@ struct WarpSolver {
     for (;;) {
       if (refactor) {
         hist = 0;  // the only call site: the inversion is ~1,400 instructions per inlined copy
-        const bool okf = factor(sm, t, t0, rho_i, a3, b3, lane);
+        const bool okf = factor(sm, t, t0, rho_i, a3, b3, lane, st.eps_abs >= wp.gather_eps);
         nfac++;
         refactor = false;
         if (!__all_sync(FULL, okf)) {

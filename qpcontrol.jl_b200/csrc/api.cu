@@ -529,6 +529,7 @@ static WarpParams warp_params() {
     w.first = (e = getenv("QPC_WARP_FIRST")) ? atoi(e) : 25;
     w.check = (e = getenv("QPC_WARP_CHECK")) ? atoi(e) : 25;  // OSQP's check_termination default; denser checks lose
     w.aitken = (e = getenv("QPC_WARP_AITKEN")) ? atoi(e) : 25;
+    w.gather_eps = (e = getenv("QPC_WARP_GATHER_EPS")) ? atof(e) : 1e-6;
     if (!(w.kappa >= 1.0)) w.kappa = 1.0;
     if (!(w.growth > 1.0)) w.growth = 1.35;
     return w;

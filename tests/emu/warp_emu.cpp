@@ -189,6 +189,7 @@ int emu_warp_solve_qp_batch(int64_t B, int32_t n, int32_t mg, int32_t nbx, const
   wp.first = first;
   wp.check = check;
   wp.aitken = aitken;
+  wp.gather_eps = 1e-6;
   std::vector<double> smem((s2421 ? WarpSolver<24, 21>::SMEM_DOUBLES : WarpSolver<30, 27>::SMEM_DOUBLES) + 8);
   for (int64_t i = 0; i < B; i++) {
     Job job;
