@@ -46,7 +46,8 @@ struct WarpParams {
   int first;      // first adaptation iteration
   int check;      // residual check interval
   int aitken;     // extrapolation of slowly converging solves every this many iterations (0 = off)
-  double gather_eps;  // the inversion gathers its pivot rows by symmetry when eps_abs >= this (see WarpSolver::factor)
+  double gather_eps;  // the inversion gathers its pivot rows by symmetry when eps_abs >= this or eps_rel >= this / 100
+                      // (measured fine down to eps_abs = eps_rel = 1e-8; not at eps_abs 1e-8 with eps_rel 1e-16: WarpSolver::factor)
 };
 
 #if defined(__CUDACC__)
@@ -169,7 +170,7 @@ struct WarpSolver {
     // rotated position, instead of sixteen 16-byte stores of lane k's registers that 31 lanes issue predicated off: the ADMM
     // stage of 16,384 solves 1.17 -> 1.01 ms.  Lane k keeps its own row, which equals the gathered one only up to the
     // asymmetry the rounding errors have built up: fine at eps 1e-5, a floor on the residuals at 1e-8 (solves stalled at the
-    // iteration limit), so tight tolerances take the broadcast (WarpParams::gather_eps).
+    // iteration limit with eps_rel = 1e-16, i.e. 1e-11 relative), so such tolerances take the broadcast (WarpParams::gather_eps).
     double s = 1.0, f = 1.0;
     bool ok = true;
     double dk_mine = rcp_pos(t[0]);
@@ -683,7 +684,7 @@ struct WarpSolver {
     for (;;) {
       if (refactor) {
         hist = 0;  // the only call site: the inversion is ~1,400 instructions per inlined copy
-        const bool okf = factor(sm, t, t0, rho_i, a3, b3, lane, st.eps_abs >= wp.gather_eps);
+        const bool okf = factor(sm, t, t0, rho_i, a3, b3, lane, st.eps_abs >= wp.gather_eps || st.eps_rel >= 1e-2 * wp.gather_eps);
         nfac++;
         refactor = false;
         if (!__all_sync(FULL, okf)) {
