@@ -127,6 +127,9 @@ struct WarpSolver {
 #endif
   }
 
+  // 1 / x for a normal x of either sign (the IEEE division is ~25 instructions, most of them for cases that cannot occur here)
+  static __device__ __forceinline__ double rcp_any(double x) { return copysign(rcp_pos(fabs(x)), x); }
+
   // x~ = t0 + T~ u for the vector u at `vec` (32 doubles, 16-byte aligned): four accumulation chains
   static __device__ __forceinline__ double row_times(const double (&t)[32], const double* vec, double t0) {
     double a0 = t0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -241,7 +244,7 @@ struct WarpSolver {
 #pragma unroll
       for (int k = 0; k < ME; k++) {
         ok = ok && (S[k][k] > 0.0);
-        const double d = 1.0 / S[k][k];
+        const double d = rcp_pos(S[k][k]);  // S is positive definite (checked just above)
 #pragma unroll
         for (int b = 0; b < ME; b++) {
           S[k][b] *= d;
@@ -388,7 +391,7 @@ struct WarpSolver {
         rb[0] = ca[0] - alpha;
 #pragma unroll
         for (int r = 1; r < MG; r++) rb[r] = ca[r];
-        rb[MG] = den > 0.0 ? 1.0 / den : 0.0;
+        rb[MG] = den > 0.0 ? rcp_pos(den) : 0.0;
       }
       __syncwarp();
       const double beta = rb[MG];
@@ -444,11 +447,12 @@ struct WarpSolver {
       if (!(dmin > 1e-11 * dmax) || !finite_val(dmax)) bad = bad ? bad : 2;
       for (int idx = lane; idx < NA * NAP; idx += 32) {
         const int s_ = idx / NAP, i = idx - s_ * NAP, r = NA - 1 - s_;
+        if (i == NAP - 1) continue;  // the reciprocals of the diagonal: below, one per lane (not a division inside this loop)
         double val = 0.0;
-        if (i == NAP - 1) val = 1.0 / RA[r * NAP + r];
-        else if (i >= s_ && i - s_ < r) val = RA[(i - s_) * NAP + r];
+        if (i >= s_ && i - s_ < r) val = RA[(i - s_) * NAP + r];
         RS[idx] = val;
       }
+      if (lane < NA) RS[(NA - 1 - lane) * NAP + NAP - 1] = rcp_any(RA[lane * NAP + lane]);
     }
     __syncwarp();
     // Back-substitution, column-oriented on ROTATING registers: at step s the entry to solve sits in register NA-1,
